@@ -1,0 +1,149 @@
+/*
+ * sar.h — C ABI of libsar.so: the B200 (sm_100a) hot path of routed multi-adapter LoRA Whisper.
+ *
+ * The reference (dhruv0811/speech-adapter-routing) has no native/FFI layer at all: its hot path is
+ * Python delegating to HF transformers + PEFT.  This header therefore *defines* the boundary a
+ * maintainer would bind (ctypes stub in INTEGRATION.md).  Each entry point names the reference
+ * code it replaces (paths relative to the reference repo; $HF = transformers/models/whisper).
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes only.  No torch types, no C++ exceptions, no abort().
+ *   - Every data pointer is a DEVICE pointer owned by the caller (PyTorch).  The library never
+ *     allocates, frees or retains caller memory.  `stream` is a cudaStream_t passed as void*;
+ *     every call is asynchronous on that stream and never synchronises.
+ *   - bf16 tensors are `uint16_t`-sized storage (torch.bfloat16), row-major, last dim contiguous.
+ *   - Return value: 0 = ok, <0 = sar_status.  sar_last_error() returns a thread-local message.
+ *   - There is NO CPU fallback: on a device that is not sm_100 every compute call returns
+ *     SAR_EARCH; without a CUDA device it returns SAR_ECUDA.
+ */
+#ifndef SAR_H_
+#define SAR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SAR_VERSION_MAJOR 0
+#define SAR_VERSION_MINOR 1
+
+/* Rank padding of the packed lora_B stack (see sar_qv_lora_fwd). */
+#define SAR_RPAD 64
+
+typedef enum sar_status {
+  SAR_OK = 0,
+  SAR_EINVAL = -1, /* bad shape / alignment / null pointer */
+  SAR_EARCH = -2,  /* device is not sm_100 (B200) */
+  SAR_ECUDA = -3,  /* CUDA runtime / launch failure */
+  SAR_EWORKSPACE = -4 /* workspace too small */
+} sar_status;
+
+/* flags for sar_qv_lora_fwd* */
+#define SAR_FLAG_NONE 0u
+#define SAR_FLAG_SAVE_U 1u /* also write u = scale*(x·A_k^T) (bf16 [B*T, r]) to ws for the backward */
+
+/* ops for sar_workspace_bytes */
+typedef enum sar_op {
+  SAR_OP_QV_LORA_FWD = 0,
+  SAR_OP_ROUTER_FWD = 1,
+  SAR_OP_QV_LORA_BWD = 2,
+  SAR_OP_QV_LORA_FWD_ROWS = 3
+} sar_op;
+
+/* Library version as major*1000+minor. */
+int sar_version(void);
+
+/* Thread-local description of the last error returned on this thread ("" if none). */
+const char* sar_last_error(void);
+
+/* 1 if the current CUDA device is sm_100 (B200), 0 if another GPU, <0 (SAR_ECUDA) if no device. */
+int sar_device_ok(void);
+
+/* Bytes of caller-provided workspace an op needs.  rows = B*T (or B for the router),
+ * d = model width, r = LoRA rank, n = n_adapters (router: n classes). Returns <0 on bad op. */
+int64_t sar_workspace_bytes(int op, int64_t rows, int64_t T, int64_t d, int64_t r, int64_t n);
+
+/*
+ * K1 — fused q/v projection with routed low-rank epilogue.
+ *   y[b,t,:] = x[b,t,:]·Wᵀ + bias + scale · (x[b,t,:]·A_kᵀ)·B_kᵀ ,  k = utt_adapter[b]  (k = -1 → base only)
+ * Replaces PEFT lora.Linear.forward at the q_proj / v_proj slots the reference injects in
+ * src/models/whisper_lora.py:88-98, invoked from $HF/modeling_whisper.py:310 (q) and :332 (v),
+ * and the per-utterance adapter selection of src/models/adapter_router.py:610-622.
+ *
+ *   x        bf16 [B, T, d_in]
+ *   W        bf16 [d_out, d_in]          (nn.Linear weight)
+ *   bias     bf16 [d_out] or NULL
+ *   A_stack  bf16 [n_adapters, r, d_in]  (lora_A of every adapter, stacked)
+ *   Bp_stack bf16 [n_adapters, d_out, SAR_RPAD]  (lora_B, columns >= r are zero padding)
+ *   utt_adapter int32 [B] or NULL (NULL → base only)
+ *   y        bf16 [B, T, d_out]
+ *   u_out    bf16 [B*T, r] or NULL — scale*(x·A_kᵀ) rounded to bf16, saved for the backward
+ * Constraints: d_in % 64 == 0, d_out % 64 == 0, r in {16,32,48,64}; all pointers 16-byte aligned.
+ * The rank-r intermediate u is rounded to bf16 once (it is an MMA operand) with `scale` already applied.
+ */
+int sar_qv_lora_fwd(const void* x, const void* W, const void* bias, const void* A_stack,
+                    const void* Bp_stack, const int32_t* utt_adapter, void* y, void* u_out,
+                    int B, int T, int d_in, int d_out, int r, int n_adapters, float scale,
+                    uint32_t flags, void* stream);
+
+/*
+ * Row-indexed variant for decode steps (T = 1 per utterance, rows of different adapters share a tile):
+ *   y[m,:] = x[m,:]·Wᵀ + bias + scale·(x[m,:]·A_kᵀ)·B_kᵀ, k = row_adapter[m].
+ * Replaces the per-sample adapter.generate loop of src/models/adapter_router.py:744-750 for the
+ * decoder self-attn q/v and cross-attn q projections at one token per utterance.
+ *   ws: workspace of sar_workspace_bytes(SAR_OP_QV_LORA_FWD_ROWS, M, 1, d, r, n) bytes.
+ */
+int sar_qv_lora_fwd_rows(const void* x, const void* W, const void* bias, const void* A_stack,
+                         const void* Bp_stack, const int32_t* row_adapter, void* y, int M,
+                         int d_in, int d_out, int r, int n_adapters, float scale, void* ws,
+                         void* stream);
+
+/*
+ * K2 — language-ID router: LayerNorm(d) per frame → mean over T → MLP(d→h1→h2→C, LN+ReLU between)
+ * → softmax → argmax, plus the adapter-index bookkeeping (stable counting sort by class).
+ * Replaces LanguageClassifier.forward/_pool_features/predict (src/models/adapter_router.py:251-312,
+ * default config: pooling="mean", use_layer_norm=True, use_cnn=False, two hidden layers) and the
+ * Python list bookkeeping of AdapterRouter.detect_language (:550-566).
+ *
+ *   h          bf16 (h_is_fp32=0) or fp32 (h_is_fp32=1) [B, T, d] encoder hidden states
+ *   ln_w,ln_b  fp32 [d]      layer_norm.{weight,bias}
+ *   W1,b1      fp32 [h1,d],[h1]   classifier.0     g1,be1 fp32 [h1]  classifier.1 (LayerNorm)
+ *   W2,b2      fp32 [h2,h1],[h2]  classifier.4     g2,be2 fp32 [h2]  classifier.5 (LayerNorm)
+ *   W3,b3      fp32 [C,h2],[C]    classifier.8
+ *   logits_out, probs_out fp32 [B,C];  idx_out int32 [B] (argmax, first maximal index on ties)
+ *   perm_out   int32 [B]   utterance indices stably sorted by idx
+ *   seg_starts_out int32 [C+1]  segment k = perm[seg_starts[k] : seg_starts[k+1]]
+ *   ws         workspace of sar_workspace_bytes(SAR_OP_ROUTER_FWD, B, T, d, 0, C) bytes
+ * Constraints: d % 8 == 0, d <= 2048, h1,h2 <= 1024, C <= 64, eps = 1e-5 for all LayerNorms.
+ */
+int sar_router_fwd(const void* h, int h_is_fp32, const float* ln_w, const float* ln_b,
+                   const float* W1, const float* b1, const float* g1, const float* be1,
+                   const float* W2, const float* b2, const float* g2, const float* be2,
+                   const float* W3, const float* b3, int B, int T, int d, int h1, int h2, int C,
+                   float* logits_out, float* probs_out, int32_t* idx_out, int32_t* perm_out,
+                   int32_t* seg_starts_out, void* ws, void* stream);
+
+/*
+ * K3 — LoRA-only backward of K1 (base W frozen):
+ *   dx      = dy·W + (scale·dy·B_k)·A_k                (skipped when dx == NULL)
+ *   dA_k   += scale · (dy·B_k)ᵀ · x      fp32 [n_adapters, r, d_in]
+ *   dB_k   += (dy)ᵀ · u                  fp32 [n_adapters, d_out, r]   (u = scale·x·A_kᵀ from the forward)
+ * Replaces autograd through PEFT lora.Linear triggered at src/training/trainer.py:251-256.
+ * dA / dB point into one flat fp32 gradient bucket that the host all-reduces with NCCL.
+ *   Wt        bf16 [d_in, d_out]  (W transposed, cached by the caller: W is frozen)
+ *   At_stack  bf16 [n_adapters, d_in, SAR_RPAD] (lora_A transposed + rank-padded)
+ *   Bt_stack  bf16 [n_adapters, r, d_out]       (lora_B transposed)
+ *   ws        workspace of sar_workspace_bytes(SAR_OP_QV_LORA_BWD, B*T, T, max(d_in,d_out), r, n_adapters)
+ */
+int sar_qv_lora_bwd(const void* dy, const void* x, const void* u, const void* Wt,
+                    const void* At_stack, const void* Bt_stack, const void* Bp_stack,
+                    const int32_t* utt_adapter, void* dx, float* dA, float* dB, int B, int T,
+                    int d_in, int d_out, int r, int n_adapters, float scale, void* ws,
+                    void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SAR_H_ */

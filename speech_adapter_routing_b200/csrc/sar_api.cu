@@ -1,0 +1,169 @@
+// sar_api.cu — the extern "C" surface of libsar.so (see include/sar.h) plus device/tensor-map plumbing.
+#include <mutex>
+#include <stdio.h>
+
+#include "sar_internal.h"
+
+namespace sar {
+
+static thread_local char g_err[512] = "";
+
+int fail(int code, const char* msg) {
+  snprintf(g_err, sizeof(g_err), "%s", msg);
+  return code;
+}
+int fail_cuda(cudaError_t e, const char* where) {
+  snprintf(g_err, sizeof(g_err), "%s: %s", where, cudaGetErrorString(e));
+  return SAR_ECUDA;
+}
+
+static std::mutex g_dev_mu;
+static DeviceInfo g_dev[64];
+static bool g_dev_init[64];
+static DeviceInfo g_nodev = {-3, -1, 0, 0, 0, 0, 0};
+
+const DeviceInfo& device_info() {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) {
+    cudaGetLastError();
+    return g_nodev;
+  }
+  std::lock_guard<std::mutex> lk(g_dev_mu);
+  if (!g_dev_init[dev]) {
+    DeviceInfo d{};
+    d.device = dev;
+    cudaDeviceGetAttribute(&d.cc_major, cudaDevAttrComputeCapabilityMajor, dev);
+    cudaDeviceGetAttribute(&d.cc_minor, cudaDevAttrComputeCapabilityMinor, dev);
+    cudaDeviceGetAttribute(&d.num_sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&d.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaDeviceGetAttribute(&d.l2_bytes, cudaDevAttrL2CacheSize, dev);
+    d.ok = (d.cc_major == 10 && d.cc_minor == 0) ? 1 : 0;
+    g_dev[dev] = d;
+    g_dev_init[dev] = true;
+  }
+  return g_dev[dev];
+}
+
+int require_sm100() {
+  const DeviceInfo& d = device_info();
+  if (d.ok < 0) return fail(SAR_ECUDA, "no CUDA device available (libsar has no CPU fallback)");
+  if (d.ok == 0) return fail(SAR_EARCH, "device is not sm_100 (B200); libsar kernels are sm_100a only");
+  return SAR_OK;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_encode = nullptr;
+static std::once_flag g_encode_once;
+
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box) {
+  std::call_once(g_encode_once, [] {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      g_encode = reinterpret_cast<EncodeTiledFn>(fn);
+  });
+  if (!g_encode) return fail(SAR_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
+  cuuint64_t gdim[5];
+  cuuint64_t gstr[5];
+  cuuint32_t bdim[5], estr[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bdim[i] = box[i];
+    estr[i] = 1;
+    if (i > 0) gstr[i - 1] = strides_bytes[i - 1];
+  }
+  CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
+                        gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled failed (CUresult %d, rank %d, dims %llu x %llu)", (int)r, rank,
+             (unsigned long long)dims[0], (unsigned long long)dims[1]);
+    return SAR_EINVAL;
+  }
+  return SAR_OK;
+}
+
+}  // namespace sar
+
+using namespace sar;
+
+extern "C" {
+
+int sar_version(void) { return SAR_VERSION_MAJOR * 1000 + SAR_VERSION_MINOR; }
+
+const char* sar_last_error(void) { return g_err; }
+
+int sar_device_ok(void) {
+  const DeviceInfo& d = device_info();
+  return d.ok < 0 ? SAR_ECUDA : d.ok;
+}
+
+int64_t sar_workspace_bytes(int op, int64_t rows, int64_t T, int64_t d, int64_t r, int64_t n) {
+  switch (op) {
+    case SAR_OP_QV_LORA_FWD: return 0;
+    case SAR_OP_ROUTER_FWD: return k2_workspace_bytes(rows, T, d);
+    case SAR_OP_QV_LORA_FWD_ROWS: return rows_workspace_bytes(rows, d, r);
+    case SAR_OP_QV_LORA_BWD: return k3_workspace_bytes(rows, T, d, r, n);
+    default: fail(SAR_EINVAL, "sar_workspace_bytes: unknown op"); return SAR_EINVAL;
+  }
+}
+
+int sar_qv_lora_fwd(const void* x, const void* W, const void* bias, const void* A_stack, const void* Bp_stack,
+                    const int32_t* utt_adapter, void* y, void* u_out, int B, int T, int d_in, int d_out, int r,
+                    int n_adapters, float scale, uint32_t flags, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  K1Args a{};
+  a.x = x; a.W = W; a.bias = bias; a.A_stack = A_stack; a.Bp_stack = Bp_stack; a.utt_adapter = utt_adapter;
+  a.y = y; a.u_out = (flags & SAR_FLAG_SAVE_U) ? u_out : nullptr;
+  a.B = B; a.T = T; a.d_in = d_in; a.d_out = d_out; a.r = r; a.n_adapters = n_adapters; a.scale = scale;
+  a.block_n_override = static_cast<int>((flags >> 8) & 0x3FF);   // debug/tuning: bits [8,18) = BLOCK_N
+  a.grid_override = static_cast<int>((flags >> 18) & 0x3FF);     // debug/tuning: bits [18,28) = grid size
+  if ((flags & SAR_FLAG_SAVE_U) && !u_out) return fail(SAR_EINVAL, "sar_qv_lora_fwd: SAVE_U without u_out");
+  return k1_qv_lora_fwd(a, static_cast<cudaStream_t>(stream));
+}
+
+int sar_qv_lora_fwd_rows(const void* x, const void* W, const void* bias, const void* A_stack, const void* Bp_stack,
+                         const int32_t* row_adapter, void* y, int M, int d_in, int d_out, int r, int n_adapters,
+                         float scale, void* ws, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  return rows_qv_lora_fwd(x, W, bias, A_stack, Bp_stack, row_adapter, y, M, d_in, d_out, r, n_adapters, scale, ws,
+                          static_cast<cudaStream_t>(stream));
+}
+
+int sar_router_fwd(const void* h, int h_is_fp32, const float* ln_w, const float* ln_b, const float* W1,
+                   const float* b1, const float* g1, const float* be1, const float* W2, const float* b2,
+                   const float* g2, const float* be2, const float* W3, const float* b3, int B, int T, int d, int h1,
+                   int h2, int C, float* logits_out, float* probs_out, int32_t* idx_out, int32_t* perm_out,
+                   int32_t* seg_starts_out, void* ws, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  K2Args a{};
+  a.h = h; a.h_is_fp32 = h_is_fp32;
+  a.ln_w = ln_w; a.ln_b = ln_b; a.W1 = W1; a.b1 = b1; a.g1 = g1; a.be1 = be1;
+  a.W2 = W2; a.b2 = b2; a.g2 = g2; a.be2 = be2; a.W3 = W3; a.b3 = b3;
+  a.B = B; a.T = T; a.d = d; a.h1 = h1; a.h2 = h2; a.C = C;
+  a.logits = logits_out; a.probs = probs_out; a.idx = idx_out; a.perm = perm_out; a.seg_starts = seg_starts_out;
+  a.ws = ws;
+  return k2_router_fwd(a, static_cast<cudaStream_t>(stream));
+}
+
+int sar_qv_lora_bwd(const void* dy, const void* x, const void* u, const void* Wt, const void* At_stack,
+                    const void* Bt_stack, const void* Bp_stack, const int32_t* utt_adapter, void* dx, float* dA,
+                    float* dB, int B, int T, int d_in, int d_out, int r, int n_adapters, float scale, void* ws,
+                    void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  K3Args a{};
+  a.dy = dy; a.x = x; a.u = u; a.Wt = Wt; a.At_stack = At_stack; a.Bt_stack = Bt_stack; a.Bp_stack = Bp_stack;
+  a.utt_adapter = utt_adapter; a.dx = dx; a.dA = dA; a.dB = dB;
+  a.B = B; a.T = T; a.d_in = d_in; a.d_out = d_out; a.r = r; a.n_adapters = n_adapters; a.scale = scale; a.ws = ws;
+  return k3_qv_lora_bwd(a, static_cast<cudaStream_t>(stream));
+}
+
+}  // extern "C"

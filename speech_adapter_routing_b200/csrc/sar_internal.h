@@ -1,0 +1,85 @@
+// sar_internal.h — shared host-side declarations of libsar (not part of the public ABI).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string.h>
+
+#include "../../include/sar.h"
+
+namespace sar {
+
+struct DeviceInfo {
+  int ok;  // 1 = sm_100, 0 = other GPU, <0 = no device
+  int device;
+  int cc_major, cc_minor;
+  int num_sms;
+  int max_smem_optin;
+  int l2_bytes;
+};
+
+// Cached per-process properties of the current device (queried once per device, thread-safe).
+const DeviceInfo& device_info();
+
+// Record an error message for sar_last_error() and return `code`.
+int fail(int code, const char* msg);
+int fail_cuda(cudaError_t e, const char* where);
+// Entry-point guard: returns SAR_OK only on an sm_100 device.
+int require_sm100();
+
+// Encode a bf16 tiled tensor map with 128-byte swizzle.  dims/box are innermost-first; strides (bytes) has rank-1
+// entries for dims 1..rank-1.  Uses cuTensorMapEncodeTiled resolved through cudaGetDriverEntryPoint, so libsar has
+// no link-time dependency on libcuda.
+int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                   const uint32_t* box);
+
+struct K1Args {
+  const void* x;
+  const void* W;
+  const void* bias;
+  const void* A_stack;
+  const void* Bp_stack;
+  const int32_t* utt_adapter;
+  void* y;
+  void* u_out;
+  int B, T, d_in, d_out, r, n_adapters;
+  float scale;
+  int block_n_override;  // 0 = auto
+  int grid_override;     // 0 = auto
+};
+int k1_qv_lora_fwd(const K1Args& a, cudaStream_t stream);
+
+struct K2Args {
+  const void* h;
+  int h_is_fp32;
+  const float *ln_w, *ln_b, *W1, *b1, *g1, *be1, *W2, *b2, *g2, *be2, *W3, *b3;
+  int B, T, d, h1, h2, C;
+  float* logits;
+  float* probs;
+  int32_t* idx;
+  int32_t* perm;
+  int32_t* seg_starts;
+  void* ws;
+};
+int64_t k2_workspace_bytes(int64_t B, int64_t T, int64_t d);
+int k2_router_fwd(const K2Args& a, cudaStream_t stream);
+
+// Row-indexed (decode-step) variant: base GEMM through K1 + per-row gathered low-rank update.
+int64_t rows_workspace_bytes(int64_t M, int64_t d, int64_t r);
+int rows_qv_lora_fwd(const void* x, const void* W, const void* bias, const void* A_stack, const void* Bp_stack,
+                     const int32_t* row_adapter, void* y, int M, int d_in, int d_out, int r, int n_adapters,
+                     float scale, void* ws, cudaStream_t stream);
+
+struct K3Args {
+  const void *dy, *x, *u, *Wt, *At_stack, *Bt_stack, *Bp_stack;
+  const int32_t* utt_adapter;
+  void* dx;
+  float *dA, *dB;
+  int B, T, d_in, d_out, r, n_adapters;
+  float scale;
+  void* ws;
+};
+int64_t k3_workspace_bytes(int64_t rows, int64_t T, int64_t d, int64_t r, int64_t n_adapters);
+int k3_qv_lora_bwd(const K3Args& a, cudaStream_t stream);
+
+}  // namespace sar

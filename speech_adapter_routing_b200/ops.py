@@ -1,0 +1,193 @@
+"""Torch-facing wrappers over the libsar C ABI.  PyTorch only provides device memory and the stream; all
+arithmetic of the hot path happens inside libsar's sm_100a kernels.  Every wrapper raises if libsar is missing or
+the tensors are not CUDA tensors — there is no eager fallback.
+"""
+from __future__ import annotations
+
+from typing import NamedTuple, Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import SAR_FLAG_SAVE_U, SAR_RPAD, check, lib
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _stream(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def _need_cuda(*ts: Optional[torch.Tensor]) -> None:
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("libsar ops need CUDA tensors (sm_100a only, no CPU fallback)")
+
+
+def _bf16c(t: Optional[torch.Tensor], name: str) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    if t.dtype != torch.bfloat16:
+        raise TypeError(f"{name} must be torch.bfloat16, got {t.dtype}")
+    return t.contiguous()
+
+
+def pack_lora_b(B_stack: torch.Tensor) -> torch.Tensor:
+    """[n_adapters, d_out, r] -> bf16 [n_adapters, d_out, SAR_RPAD] with zero rank padding (kernel operand layout)."""
+    n, d_out, r = B_stack.shape
+    if r > SAR_RPAD:
+        raise ValueError(f"rank {r} > {SAR_RPAD} is not supported")
+    out = torch.zeros(n, d_out, SAR_RPAD, dtype=torch.bfloat16, device=B_stack.device)
+    out[:, :, :r] = B_stack.to(torch.bfloat16)
+    return out
+
+
+def pad_rank16(A_stack: torch.Tensor, B_stack: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor, int]:
+    """Zero-pad the rank to a multiple of 16 (MMA K granularity).  A [n,r,d_in], B [n,d_out,r]."""
+    r = A_stack.shape[1]
+    rp = (r + 15) // 16 * 16
+    if rp == r:
+        return A_stack, B_stack, r
+    A2 = torch.zeros(A_stack.shape[0], rp, A_stack.shape[2], dtype=A_stack.dtype, device=A_stack.device)
+    A2[:, :r] = A_stack
+    B2 = torch.zeros(B_stack.shape[0], B_stack.shape[1], rp, dtype=B_stack.dtype, device=B_stack.device)
+    B2[:, :, :r] = B_stack
+    return A2, B2, rp
+
+
+def qv_lora_fwd(x: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], A_stack: Optional[torch.Tensor],
+                Bp_stack: Optional[torch.Tensor], utt_adapter: Optional[torch.Tensor], scale: float,
+                save_u: bool = False, block_n: int = 0, grid: int = 0,
+                out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+    """K1: y = x·Wᵀ + bias + (scale·x·A_kᵀ)·B_kᵀ with k = utt_adapter[b].  x is [B, T, d_in] bf16."""
+    _need_cuda(x, W, bias, A_stack, Bp_stack, utt_adapter)
+    if x.dim() != 3:
+        raise ValueError("x must be [B, T, d_in]")
+    x = _bf16c(x, "x"); W = _bf16c(W, "W"); bias = _bf16c(bias, "bias")
+    A_stack = _bf16c(A_stack, "A_stack"); Bp_stack = _bf16c(Bp_stack, "Bp_stack")
+    B, T, d_in = x.shape
+    d_out = W.shape[0]
+    if W.shape[1] != d_in:
+        raise ValueError("W must be [d_out, d_in]")
+    n_adapters, r = 0, 16
+    if A_stack is not None and utt_adapter is not None:
+        n_adapters, r = A_stack.shape[0], A_stack.shape[1]
+        if A_stack.shape[2] != d_in or tuple(Bp_stack.shape) != (n_adapters, d_out, SAR_RPAD):
+            raise ValueError("A_stack must be [n,r,d_in] and Bp_stack [n,d_out,64]")
+        if utt_adapter.dtype != torch.int32 or utt_adapter.numel() != B:
+            raise ValueError("utt_adapter must be int32 [B]")
+        utt_adapter = utt_adapter.contiguous()
+    y = out if out is not None else torch.empty(B, T, d_out, dtype=torch.bfloat16, device=x.device)
+    u = torch.empty(B * T, r, dtype=torch.bfloat16, device=x.device) if (save_u and n_adapters) else None
+    flags = (SAR_FLAG_SAVE_U if u is not None else 0) | ((block_n & 0x3FF) << 8) | ((grid & 0x3FF) << 18)
+    check(lib().sar_qv_lora_fwd(_ptr(x), _ptr(W), _ptr(bias), _ptr(A_stack), _ptr(Bp_stack),
+                                _ptr(utt_adapter) if n_adapters else None, _ptr(y), _ptr(u), B, T, d_in, d_out, r,
+                                n_adapters, float(scale), flags, _stream(x)))
+    return y, u
+
+
+def qv_lora_fwd_rows(x: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], A_stack: Optional[torch.Tensor],
+                     Bp_stack: Optional[torch.Tensor], row_adapter: Optional[torch.Tensor],
+                     scale: float) -> torch.Tensor:
+    """Row-indexed K1 variant (decode steps): x [M, d_in], row_adapter int32 [M]."""
+    _need_cuda(x, W, bias, A_stack, Bp_stack, row_adapter)
+    x = _bf16c(x, "x"); W = _bf16c(W, "W"); bias = _bf16c(bias, "bias")
+    A_stack = _bf16c(A_stack, "A_stack"); Bp_stack = _bf16c(Bp_stack, "Bp_stack")
+    M, d_in = x.shape
+    d_out = W.shape[0]
+    n_adapters, r = 0, 16
+    if A_stack is not None and row_adapter is not None:
+        n_adapters, r = A_stack.shape[0], A_stack.shape[1]
+        if row_adapter.dtype != torch.int32 or row_adapter.numel() != M:
+            raise ValueError("row_adapter must be int32 [M]")
+        row_adapter = row_adapter.contiguous()
+    y = torch.empty(M, d_out, dtype=torch.bfloat16, device=x.device)
+    check(lib().sar_qv_lora_fwd_rows(_ptr(x), _ptr(W), _ptr(bias), _ptr(A_stack), _ptr(Bp_stack),
+                                     _ptr(row_adapter) if n_adapters else None, _ptr(y), M, d_in, d_out, r,
+                                     n_adapters, float(scale), None, _stream(x)))
+    return y
+
+
+class RouterOut(NamedTuple):
+    logits: torch.Tensor      # fp32 [B, C]
+    probs: torch.Tensor       # fp32 [B, C]
+    idx: torch.Tensor         # int32 [B]  argmax class = adapter index
+    perm: torch.Tensor        # int32 [B]  utterances stably sorted by idx
+    seg_starts: torch.Tensor  # int32 [C+1]
+
+
+class RouterParams(NamedTuple):
+    """fp32 contiguous CUDA tensors of the default LanguageClassifier (reference state-dict keys in comments)."""
+    ln_w: torch.Tensor   # layer_norm.weight
+    ln_b: torch.Tensor   # layer_norm.bias
+    W1: torch.Tensor     # classifier.0.weight
+    b1: torch.Tensor     # classifier.0.bias
+    g1: torch.Tensor     # classifier.1.weight
+    be1: torch.Tensor    # classifier.1.bias
+    W2: torch.Tensor     # classifier.4.weight
+    b2: torch.Tensor     # classifier.4.bias
+    g2: torch.Tensor     # classifier.5.weight
+    be2: torch.Tensor    # classifier.5.bias
+    W3: torch.Tensor     # classifier.8.weight
+    b3: torch.Tensor     # classifier.8.bias
+
+    @staticmethod
+    def from_state_dict(sd, device) -> "RouterParams":
+        keys = ["layer_norm.weight", "layer_norm.bias", "classifier.0.weight", "classifier.0.bias",
+                "classifier.1.weight", "classifier.1.bias", "classifier.4.weight", "classifier.4.bias",
+                "classifier.5.weight", "classifier.5.bias", "classifier.8.weight", "classifier.8.bias"]
+        return RouterParams(*[sd[k].detach().to(device=device, dtype=torch.float32).contiguous() for k in keys])
+
+
+def router_fwd(h: torch.Tensor, p: RouterParams) -> RouterOut:
+    """K2: LayerNorm → mean over T → MLP → softmax → argmax → (idx, perm, seg_starts).  h is [B,T,d] bf16 or fp32."""
+    _need_cuda(h, *p)
+    if h.dim() != 3:
+        raise ValueError("h must be [B, T, d]")
+    if h.dtype not in (torch.bfloat16, torch.float32):
+        raise TypeError("h must be bf16 or fp32")
+    h = h.contiguous()
+    B, T, d = h.shape
+    h1, h2, C = p.W1.shape[0], p.W2.shape[0], p.W3.shape[0]
+    dev = h.device
+    logits = torch.empty(B, C, dtype=torch.float32, device=dev)
+    probs = torch.empty(B, C, dtype=torch.float32, device=dev)
+    idx = torch.empty(B, dtype=torch.int32, device=dev)
+    perm = torch.empty(B, dtype=torch.int32, device=dev)
+    seg = torch.empty(C + 1, dtype=torch.int32, device=dev)
+    nbytes = lib().sar_workspace_bytes(_lib.SAR_OP_ROUTER_FWD, B, T, d, 0, C)
+    if nbytes < 0:
+        check(int(nbytes))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    check(lib().sar_router_fwd(_ptr(h), int(h.dtype == torch.float32), *[_ptr(t) for t in p], B, T, d, h1, h2, C,
+                               _ptr(logits), _ptr(probs), _ptr(idx), _ptr(perm), _ptr(seg), _ptr(ws), _stream(h)))
+    return RouterOut(logits, probs, idx, perm, seg)
+
+
+def qv_lora_bwd(dy: torch.Tensor, x: torch.Tensor, u: torch.Tensor, Wt: torch.Tensor, At_stack: torch.Tensor,
+                Bt_stack: torch.Tensor, utt_adapter: torch.Tensor, dA: torch.Tensor, dB: torch.Tensor, scale: float,
+                need_dx: bool = True) -> Optional[torch.Tensor]:
+    """K3: dx = dy·W + (scale·dy·B_k)·A_k; dA += vᵀx; dB += dyᵀu (accumulating into fp32 dA [n,r,d_in], dB [n,d_out,r]).
+
+    Wt [d_in,d_out] = Wᵀ, At_stack [n,d_in,64] = rank-padded lora_Aᵀ, Bt_stack [n,r,d_out] = lora_Bᵀ (all bf16).
+    """
+    _need_cuda(dy, x, u, Wt, At_stack, Bt_stack, utt_adapter, dA, dB)
+    dy = _bf16c(dy, "dy"); x = _bf16c(x, "x"); u = _bf16c(u, "u")
+    B, T, d_out = dy.shape
+    d_in = x.shape[-1]
+    n, r = Bt_stack.shape[0], Bt_stack.shape[1]
+    if dA.dtype != torch.float32 or dB.dtype != torch.float32 or not dA.is_contiguous() or not dB.is_contiguous():
+        raise TypeError("dA/dB must be contiguous fp32")
+    if tuple(dA.shape) != (n, r, d_in) or tuple(dB.shape) != (n, d_out, r):
+        raise ValueError("dA must be [n,r,d_in], dB [n,d_out,r]")
+    dx = torch.empty(B, T, d_in, dtype=torch.bfloat16, device=dy.device) if need_dx else None
+    nbytes = lib().sar_workspace_bytes(_lib.SAR_OP_QV_LORA_BWD, B * T, T, max(d_in, d_out), r, n)
+    if nbytes < 0:
+        check(int(nbytes))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dy.device)
+    check(lib().sar_qv_lora_bwd(_ptr(dy), _ptr(x), _ptr(u), _ptr(Wt.contiguous()), _ptr(At_stack.contiguous()),
+                                _ptr(Bt_stack.contiguous()), None, _ptr(utt_adapter.contiguous()), _ptr(dx), _ptr(dA),
+                                _ptr(dB), B, T, d_in, d_out, r, n, float(scale), _ptr(ws), _stream(dy)))
+    return dx
