@@ -416,7 +416,7 @@ int k1_qv_lora_fwd(const K1Args& a, cudaStream_t stream) {
        reinterpret_cast<uintptr_t>(a.bias) | reinterpret_cast<uintptr_t>(a.u_out)) & 15)
     return fail(SAR_EINVAL, "k1: pointers must be 16-byte aligned");
   int bn = a.block_n_override;
-  if (bn == 0) bn = (a.d_out % 192 == 0) ? 192 : 128;
+  if (bn == 0) bn = (a.d_out % 192 == 0) ? 192 : (a.d_out % 128 == 0) ? 128 : 64;
   if (a.d_out % bn) return fail(SAR_EINVAL, "k1: d_out not divisible by BLOCK_N");
   switch (bn) {
     case 64: return k1_launch<64>(a, stream);
