@@ -1,0 +1,54 @@
+"""Per-batch adapter-index bookkeeping.
+
+HF's WhisperAttention passes nothing down to ``q_proj`` / ``v_proj`` except the hidden states, so the routed
+adapter index reaches the projection modules out of band: a thread-local context that the router / wrapper sets
+for the duration of one forward.  The value is a *device* int32 tensor ``utt_adapter[B]`` (−1 = base weights
+only), written by the K2 router kernel — nothing is copied to the host, unlike the reference's
+``[self.languages[l.item()] for l in labels]`` (src/models/adapter_router.py:565).
+"""
+from __future__ import annotations
+
+import threading
+from contextlib import contextmanager
+from typing import Optional
+
+import torch
+
+
+class _RoutingState(threading.local):
+    def __init__(self) -> None:
+        self.utt_adapter: Optional[torch.Tensor] = None
+        self.active = False
+
+
+_state = _RoutingState()
+
+
+def current_utt_adapter() -> Optional[torch.Tensor]:
+    """int32 [B] device tensor set by ``route(...)``, or None when no routing context is active."""
+    return _state.utt_adapter if _state.active else None
+
+
+def routing_active() -> bool:
+    return _state.active
+
+
+@contextmanager
+def route(utt_adapter: Optional[torch.Tensor]):
+    """Run the enclosed forward with per-utterance adapter indices.  ``None`` restores module defaults
+    (every utterance uses the module's active adapter)."""
+    if utt_adapter is not None:
+        if utt_adapter.dtype != torch.int32:
+            utt_adapter = utt_adapter.to(torch.int32)
+        utt_adapter = utt_adapter.contiguous()
+    prev = (_state.utt_adapter, _state.active)
+    _state.utt_adapter, _state.active = utt_adapter, utt_adapter is not None
+    try:
+        yield
+    finally:
+        _state.utt_adapter, _state.active = prev
+
+
+def base_only(batch_size: int, device) -> torch.Tensor:
+    """utt_adapter selecting no adapter for every utterance (the LID feature pass runs on base weights)."""
+    return torch.full((batch_size,), -1, dtype=torch.int32, device=device)
