@@ -282,7 +282,7 @@ class AdapterRouter(nn.Module):
     so only ONE copy of Whisper is resident instead of n_adapters + 1.
     """
 
-    def __init__(self, base_model: nn.Module, adapters: Dict[str, Union[nn.Module, str, Path]],
+    def __init__(self, base_model: nn.Module, adapters: Optional[Dict[str, Union[nn.Module, str, Path]]],
                  classifier: LanguageClassifier, languages: List[str], strategy: str = "hard",
                  threshold: float = 0.7):
         super().__init__()
@@ -300,8 +300,25 @@ class AdapterRouter(nn.Module):
         self._install_adapters(adapters)
         self.feature_extractor = EncoderFeatureExtractor(base_model)
 
+    @classmethod
+    def from_stacked(cls, base_model: nn.Module, classifier: LanguageClassifier, languages: List[str],
+                     strategy: str = "hard", threshold: float = 0.7) -> "AdapterRouter":
+        """Router over a base model whose q_proj / v_proj already hold one adapter per language, named and
+        ordered like ``languages`` (e.g. built with ``inject_lora`` / ``PeftModel.load_adapter``)."""
+        return cls(base_model, None, classifier, languages, strategy, threshold)
+
     # ---- adapter stacking ------------------------------------------------------------------------------
     def _install_adapters(self, adapters) -> None:
+        if adapters is None:
+            mods = lora_modules(self.whisper)
+            if not mods:
+                raise ValueError("base model holds no LoRA layers")
+            for m in mods.values():
+                if m.adapter_order != self.languages:
+                    raise ValueError(f"adapter stack {m.adapter_order} != languages {self.languages}")
+                for p in list(m.lora_A.parameters()) + list(m.lora_B.parameters()):
+                    p.requires_grad = False
+            return
         missing = [l for l in self.languages if l not in adapters]
         if missing:
             raise KeyError(f"no adapter given for languages {missing}")

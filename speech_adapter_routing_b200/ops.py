@@ -12,6 +12,16 @@ from . import _lib
 from ._lib import SAR_FLAG_SAVE_U, SAR_RPAD, check, lib
 
 
+# ---- instrumentation used by bench.py: kernel-launch counts and (optional) per-launch CUDA-event timing ----------
+LAUNCHES = {"k1": 0, "k2": 0, "k3": 0, "rows": 0}   # kernels launched by libsar, by op (k2 = 2, k3 = 3, rows = 2)
+K1_TIMELINE = None   # set to a list to record (B*T, d_in, d_out, r, has_lora, start_event, end_event) per K1 call
+
+
+def reset_counters() -> None:
+    for k in LAUNCHES:
+        LAUNCHES[k] = 0
+
+
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
     return None if t is None else t.data_ptr()
 
@@ -82,9 +92,18 @@ def qv_lora_fwd(x: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], 
     y = out if out is not None else torch.empty(B, T, d_out, dtype=torch.bfloat16, device=x.device)
     u = torch.empty(B * T, r, dtype=torch.bfloat16, device=x.device) if (save_u and n_adapters) else None
     flags = (SAR_FLAG_SAVE_U if u is not None else 0) | ((block_n & 0x3FF) << 8) | ((grid & 0x3FF) << 18)
+    tl = K1_TIMELINE
+    if tl is not None:
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev0.record()
     check(lib().sar_qv_lora_fwd(_ptr(x), _ptr(W), _ptr(bias), _ptr(A_stack), _ptr(Bp_stack),
                                 _ptr(utt_adapter) if n_adapters else None, _ptr(y), _ptr(u), B, T, d_in, d_out, r,
                                 n_adapters, float(scale), flags, _stream(x)))
+    if tl is not None:
+        ev1.record()
+        tl.append((B * T, d_in, d_out, r, n_adapters > 0, ev0, ev1))
+    LAUNCHES["k1"] += 1
     return y, u
 
 
@@ -107,6 +126,7 @@ def qv_lora_fwd_rows(x: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tens
     check(lib().sar_qv_lora_fwd_rows(_ptr(x), _ptr(W), _ptr(bias), _ptr(A_stack), _ptr(Bp_stack),
                                      _ptr(row_adapter) if n_adapters else None, _ptr(y), M, d_in, d_out, r,
                                      n_adapters, float(scale), None, _stream(x)))
+    LAUNCHES["rows"] += 2 if n_adapters else 1
     return y
 
 
@@ -163,6 +183,7 @@ def router_fwd(h: torch.Tensor, p: RouterParams) -> RouterOut:
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
     check(lib().sar_router_fwd(_ptr(h), int(h.dtype == torch.float32), *[_ptr(t) for t in p], B, T, d, h1, h2, C,
                                _ptr(logits), _ptr(probs), _ptr(idx), _ptr(perm), _ptr(seg), _ptr(ws), _stream(h)))
+    LAUNCHES["k2"] += 2
     return RouterOut(logits, probs, idx, perm, seg)
 
 
@@ -190,4 +211,5 @@ def qv_lora_bwd(dy: torch.Tensor, x: torch.Tensor, u: torch.Tensor, Wt: torch.Te
     check(lib().sar_qv_lora_bwd(_ptr(dy), _ptr(x), _ptr(u), _ptr(Wt.contiguous()), _ptr(At_stack.contiguous()),
                                 _ptr(Bt_stack.contiguous()), None, _ptr(utt_adapter.contiguous()), _ptr(dx), _ptr(dA),
                                 _ptr(dB), B, T, d_in, d_out, r, n, float(scale), _ptr(ws), _stream(dy)))
+    LAUNCHES["k3"] += 3
     return dx
