@@ -1,0 +1,92 @@
+"""Data-parallel host logic on CPU: utterance sharding and the flat LoRA-gradient bucket all-reduce, exercised with
+world_size = 2 over gloo (the GPU path uses the same code with NCCL)."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from speech_adapter_routing_b200.dist import FlatGradBucket, shard_batch, shard_range
+
+
+def test_shard_range_is_contiguous_balanced_and_complete():
+    for n in (0, 1, 7, 64, 65, 512):
+        for world in (1, 2, 3, 4, 8):
+            spans = [shard_range(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(world - 1))
+            sizes = [e - s for s, e in spans]
+            assert max(sizes) - min(sizes) <= 1
+    with pytest.raises(ValueError):
+        shard_range(4, 2, 2)
+
+
+def test_shard_batch_without_process_group_is_identity():
+    t = torch.arange(10).reshape(5, 2)
+    assert torch.equal(shard_batch(t), t)
+    assert torch.equal(shard_batch(t, 2, 1), t[3:])
+
+
+def test_flat_bucket_views_alias_param_grads():
+    ps = [torch.nn.Parameter(torch.randn(3, 4)), torch.nn.Parameter(torch.randn(5))]
+    b = FlatGradBucket(ps)
+    assert b.buffer.numel() == 17
+    (ps[0].sum() * 2 + ps[1].sum() * 3).backward()     # AccumulateGrad adds in place into the views
+    assert torch.equal(b.buffer, torch.cat([torch.full((5,), 3.0), torch.full((12,), 2.0)]))   # reverse order
+    assert ps[0].grad.data_ptr() == b.views[1].data_ptr()
+    n = b.clip_grad_norm_(1.0)
+    assert torch.allclose(n, torch.tensor((5 * 9 + 12 * 4) ** 0.5))
+    assert torch.allclose(torch.linalg.vector_norm(b.buffer), torch.tensor(1.0), atol=1e-5)
+    b.zero_()
+    assert float(b.buffer.abs().sum()) == 0.0 and ps[1].grad is b.views[0]
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)                      # identical replicas
+        A = torch.nn.Parameter(torch.randn(4, 6))
+        Bm = torch.nn.Parameter(torch.randn(6, 4))
+        bucket = FlatGradBucket([A, Bm])
+        # global batch of 5 "utterances", sharded 3 / 2; loss = mean over the GLOBAL batch
+        g = torch.Generator().manual_seed(1)
+        x = torch.randn(5, 6, generator=g)
+        xs = shard_batch(x)
+        assert xs.shape[0] == (3 if rank == 0 else 2)
+        bucket.zero_()
+        loss = ((xs @ A.t()) @ Bm.t()).pow(2).sum() / 5 * world   # local sum scaled so that the rank-mean is the global mean
+        loss.backward()
+        h = bucket.all_reduce_mean(async_op=True)
+        h.wait()
+        # single-process gradient on the concatenated batch
+        A1 = A.detach().clone().requires_grad_(True)
+        B1 = Bm.detach().clone().requires_grad_(True)
+        (((x @ A1.t()) @ B1.t()).pow(2).sum() / 5).backward()
+        ok = torch.allclose(A.grad, A1.grad, atol=1e-5) and torch.allclose(Bm.grad, B1.grad, atol=1e-5)
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_allreduced_grads_equal_single_process_grads():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(results) == [(0, True), (1, True)]

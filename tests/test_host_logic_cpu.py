@@ -1,0 +1,201 @@
+"""Host-side mirror of the reference API: module injection, PEFT checkpoint layout, routing context, router
+checkpoint format, aggregation semantics.  No GPU and no kernel calls."""
+import json
+from pathlib import Path
+
+import pytest
+import torch
+import torch.nn as nn
+
+import speech_adapter_routing_b200 as sar
+from oracle import fixtures, router as orouter, whisper as owhisper
+from speech_adapter_routing_b200 import lid_router, routing
+from speech_adapter_routing_b200.peft_compat import ADAPTER_CONFIG, ADAPTER_WEIGHTS
+
+
+@pytest.fixture(scope="module")
+def micro_model():
+    return owhisper.build_whisper("micro")
+
+
+def test_injection_targets_every_q_and_v_proj(micro_model):
+    import copy
+    m = copy.deepcopy(micro_model)
+    paths = sar.inject_lora(m, sar.LoraConfig(r=16, lora_alpha=32, target_modules=["q_proj", "v_proj"]))
+    L = m.config.encoder_layers
+    assert len(paths) == 2 * L + 4 * L          # enc self-attn q,v + dec self-attn q,v + dec cross-attn q,v
+    assert all(p.endswith(("q_proj", "v_proj")) for p in paths)
+    assert not any("k_proj" in p or "out_proj" in p for p in paths)
+    mod = m.get_submodule(paths[0])
+    assert isinstance(mod, sar.RoutedLoRALinear)
+    # PEFT defaults: A kaiming-uniform, B zero; adapters fp32; base frozen
+    assert torch.count_nonzero(mod.lora_B["default"].weight) == 0
+    assert mod.lora_A["default"].weight.dtype == torch.float32
+    assert not mod.base_layer.weight.requires_grad and mod.lora_A["default"].weight.requires_grad
+
+
+def test_peft_model_attribute_paths_and_trainable_set(micro_model):
+    import copy
+    pm = sar.get_peft_model(copy.deepcopy(micro_model), sar.LoraConfig(r=8, lora_alpha=16,
+                                                                        target_modules=["q_proj", "v_proj"]))
+    # paths the reference walks: whisper_lora.py:168-184 and adapter_router.py:425-437
+    assert pm.base_model.model.model.encoder.gradient_checkpointing in (True, False)
+    pm.base_model.model.gradient_checkpointing_enable()
+    assert pm.base_model.model.model.encoder.gradient_checkpointing
+    pm.base_model.model.gradient_checkpointing_disable()
+    assert pm.config.use_cache in (True, False)
+    names = [n for n, p in pm.named_parameters() if p.requires_grad]
+    assert names and all(".lora_A." in n or ".lora_B." in n for n in names)
+    # trainer's weight-decay grouping (trainer.py:112-118) relies on these substrings being absent
+    assert not any(s in n for n in names for s in ("bias", "LayerNorm", "layer_norm"))
+    d, r, L = micro_model.config.d_model, 8, micro_model.config.encoder_layers
+    assert sum(p.numel() for p in pm.parameters() if p.requires_grad) == 6 * L * 2 * r * d
+
+
+def test_save_pretrained_writes_peft_layout_and_round_trips(tmp_path, micro_model):
+    import copy
+    from safetensors.torch import load_file
+
+    pm = sar.get_peft_model(copy.deepcopy(micro_model), sar.LoraConfig(r=16, lora_alpha=32,
+                                                                        target_modules=["q_proj", "v_proj"]))
+    with torch.no_grad():
+        for m in sar.lora_modules(pm).values():
+            m.lora_B["default"].weight.normal_(0, 0.02)
+    pm.save_pretrained(tmp_path / "ad")
+    assert sorted(p.name for p in (tmp_path / "ad").iterdir()) == [ADAPTER_CONFIG, ADAPTER_WEIGHTS]
+    cfg = json.loads((tmp_path / "ad" / ADAPTER_CONFIG).read_text())
+    for k, v in {"peft_type": "LORA", "task_type": None, "r": 16, "lora_alpha": 32, "bias": "none",
+                 "fan_in_fan_out": False, "modules_to_save": None, "use_rslora": False, "use_dora": False}.items():
+        assert cfg[k] == v
+    assert sorted(cfg["target_modules"]) == ["q_proj", "v_proj"]
+    sd = load_file(str(tmp_path / "ad" / ADAPTER_WEIGHTS))
+    key = "base_model.model.model.encoder.layers.0.self_attn.q_proj.lora_A.weight"   # adapter name elided
+    assert key in sd and sd[key].shape == (16, micro_model.config.d_model)
+    assert all(k.startswith("base_model.model.model.") and k.endswith((".lora_A.weight", ".lora_B.weight")) for k in sd)
+    # reload into a fresh base model
+    pm2 = sar.PeftModel.from_pretrained(copy.deepcopy(micro_model), tmp_path / "ad")
+    a, b = pm.state_dict(), pm2.state_dict()
+    assert a.keys() == b.keys()
+    assert all(torch.equal(a[k], b[k]) for k in a)
+
+
+def test_reader_accepts_an_independently_written_peft_adapter(tmp_path, micro_model):
+    import copy
+    weights = owhisper.make_adapter_weights(micro_model, 16, 3)
+    owhisper.write_peft_adapter(tmp_path / "x", weights, k=2, r=16, lora_alpha=32)
+    pm = sar.PeftModel.from_pretrained(copy.deepcopy(micro_model), tmp_path / "x")
+    for path, (A, B) in weights.items():
+        m = pm.base_model.model.get_submodule(path)
+        assert torch.equal(m.lora_A["default"].weight, A[2]) and torch.equal(m.lora_B["default"].weight, B[2])
+        assert m.scaling["default"] == 2.0
+
+
+def test_merge_and_unload_folds_the_adapter(micro_model):
+    import copy
+    pm = sar.get_peft_model(copy.deepcopy(micro_model), sar.LoraConfig(r=4, lora_alpha=8, target_modules=["q_proj"]))
+    m = next(iter(sar.lora_modules(pm).values()))
+    with torch.no_grad():
+        m.lora_B["default"].weight.normal_(0, 0.02)
+    W = m.base_layer.weight + 2.0 * m.lora_B["default"].weight @ m.lora_A["default"].weight
+    merged = pm.merge_and_unload()
+    assert not sar.lora_modules(merged)
+    q = merged.model.encoder.layers[0].self_attn.q_proj
+    assert isinstance(q, nn.Linear) and torch.allclose(q.weight, W, atol=1e-6)
+
+
+def test_routed_linear_has_no_cpu_fallback():
+    lin = nn.Linear(64, 64)
+    m = sar.RoutedLoRALinear(lin, "a", r=16, lora_alpha=32)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m(torch.zeros(1, 4, 64))
+
+
+def test_routing_context_is_scoped_and_nested():
+    assert routing.current_utt_adapter() is None
+    a = torch.tensor([0, 1], dtype=torch.int64)
+    with sar.route(a):
+        cur = routing.current_utt_adapter()
+        assert cur.dtype == torch.int32 and cur.tolist() == [0, 1]
+        with sar.route(None):
+            assert routing.current_utt_adapter() is None
+        assert routing.current_utt_adapter().tolist() == [0, 1]
+    assert routing.current_utt_adapter() is None
+    assert sar.base_only(3, "cpu").tolist() == [-1, -1, -1]
+
+
+def test_language_classifier_checkpoint_format_and_state_dict_keys(tmp_path):
+    clf = sar.LanguageClassifier(input_dim=64, num_classes=4, languages=["hi", "it", "pa", "te"],
+                                 class_weights=[1.0, 2.0, 1.0, 0.5])
+    # with class weights the reference's state dict also carries the buffer and CrossEntropyLoss's copy of it
+    assert set(clf.state_dict()) == set(fixtures.ROUTER_KEYS) | {"_class_weights", "loss_fn.weight"}
+    assert set(sar.LanguageClassifier(input_dim=64, num_classes=4).state_dict()) == set(fixtures.ROUTER_KEYS)
+    clf.save(tmp_path / "c" / "classifier.pt")
+    ck = torch.load(tmp_path / "c" / "classifier.pt", weights_only=False)
+    assert set(ck) == {"state_dict", "config"}
+    assert set(ck["config"]) == {"input_dim", "num_classes", "pooling", "use_cnn", "label_smoothing", "languages",
+                                 "class_weights"}
+    clf2 = sar.LanguageClassifier.load(tmp_path / "c" / "classifier.pt")
+    assert clf2.languages == ["hi", "it", "pa", "te"]
+    assert all(torch.equal(v, clf2.state_dict()[k]) for k, v in clf.state_dict().items())
+
+
+def test_language_classifier_torch_graph_matches_reference_golden():
+    """The training/CPU graph of the mirror class reproduces the REFERENCE class's outputs on its golden vectors."""
+    g = torch.load(Path(__file__).parent / "golden" / "router_golden.pt")
+    for c in g["cases"]:
+        clf = sar.LanguageClassifier(input_dim=c["d"], num_classes=c["C"]).eval()
+        clf.load_state_dict(c["state_dict"])
+        with torch.no_grad():
+            out = clf(c["h"].float())
+        assert torch.allclose(out["logits"], c["logits"], atol=1e-6)
+        labels, probs = clf.predict(c["h"].float())
+        assert torch.equal(labels, c["labels"]) and torch.allclose(probs, c["predict_probs"], atol=1e-7)
+        names, _ = clf.predict_language(c["h"].float())
+        assert names == [clf.idx_to_lang[i] for i in c["labels"].tolist()]
+
+
+def test_class_weight_strategies():
+    w = sar.LanguageClassifier.compute_class_weights_from_counts({"a": 100, "b": 10}, ["a", "b"])
+    assert torch.allclose(w, torch.tensor([0.55 / 3.025, 5.5 / 3.025]), atol=1e-4)
+    w = sar.LanguageClassifier.compute_class_weights_from_counts({"a": 100, "b": 1}, ["a", "b"], max_weight=1.5)
+    # [0.505, 50.5] -> /mean -> [0.0198, 1.9802] -> clamp 1.5 -> /mean -> [0.02606, 1.97394]
+    assert torch.allclose(w, torch.tensor([0.02606, 1.97394]), atol=1e-4)
+    with pytest.raises(ValueError):
+        sar.LanguageClassifier.compute_class_weights_from_counts({"a": 1}, ["a"], strategy="nope")
+
+
+def test_per_utterance_loss_is_mean_of_per_sample_means():
+    """Reference aggregation (adapter_router.py:707) — not HF's batch token-mean."""
+    g = torch.Generator().manual_seed(0)
+    logits = torch.randn(3, 5, 11, generator=g)
+    labels = torch.randint(0, 11, (3, 5), generator=g)
+    labels[1, 3:] = -100
+    want = torch.stack([torch.nn.functional.cross_entropy(logits[i], labels[i], ignore_index=-100)
+                        for i in range(3)]).mean()
+    assert torch.allclose(lid_router._per_utterance_loss(logits, labels), want, atol=1e-6)
+
+
+def test_zero_pad_after_eos_matches_per_sample_generate_padding():
+    eos = 3
+    ids = torch.tensor([[4, 9, 8, 3, 1, 1], [4, 7, 3, 1, 1, 1], [4, 5, 6, 7, 8, 9]])
+    out = lid_router._zero_pad_after_eos(ids, eos)
+    assert out.tolist() == [[4, 9, 8, 3, 0, 0], [4, 7, 3, 0, 0, 0], [4, 5, 6, 7, 8, 9]]
+    ids = torch.tensor([[4, 9, 3, 1], [4, 3, 1, 1]])
+    assert lid_router._zero_pad_after_eos(ids, eos).tolist() == [[4, 9, 3], [4, 3, 0]]
+
+
+def test_whisper_lora_wrapper_api_offline(monkeypatch):
+    monkeypatch.setenv("SAR_RANDOM_INIT", "1")
+    w = sar.WhisperLoRA("whisper-tiny", lora_r=8, lora_alpha=16, lora_dropout=0.0, language="hindi", device="cpu")
+    assert w.model_name == "openai/whisper-tiny" and w.language == "hindi" and w.task == "transcribe"
+    assert w.lora_config.r == 8 and w.lora_config.target_modules == ["q_proj", "v_proj"]
+    assert w.model.base_model.model.model.encoder.gradient_checkpointing      # default use_gradient_checkpointing
+    assert w.model.config.use_cache is False
+    assert w.train() is w and w.eval() is w
+    fx = sar.EncoderFeatureExtractor(w)
+    assert fx.get_hidden_dim() == 384
+    assert fx._get_encoder() is w.model.base_model.model.model.encoder
+    w2 = sar.create_whisper_lora("whisper-tiny", {"r": 4, "lora_alpha": 8, "lora_dropout": 0.0}, device="cpu")
+    assert w2.lora_config.r == 4
+    assert sar.get_model_name("whisper-large") == "openai/whisper-large-v3"
+    assert sar.get_model_info("whisper-small")["hidden_size"] == 768

@@ -1,0 +1,287 @@
+"""End-to-end GPU parity of the drop-in Python API (RoutedLoRALinear / WhisperLoRA / AdapterRouter) against the CPU
+oracle of the reference's routed forward (oracle/whisper.py) on identical seeded synthetic inputs.
+
+Gates (north star): router adapter indices BIT-EXACT; every LoRA'd module output and the final logits within a
+stated bf16 tolerance of the fp32 oracle; identical greedy token sequences on the check set.
+
+Tolerances: the GPU path stores activations in bf16 (2^-8 relative rounding per op) through 2·L layers, the oracle
+is fp32 end to end.  Per LoRA'd module output: max|err| <= 4e-2 * max|ref|; logits: max|err| <= 5e-2 * max|ref|.
+"""
+import copy
+from pathlib import Path
+
+import pytest
+import torch
+
+import speech_adapter_routing_b200 as sar
+from oracle import fixtures, lora as olora, router as orouter, whisper as owhisper
+
+pytestmark = pytest.mark.gpu
+
+MODULE_TOL = 4e-2
+LOGIT_TOL = 5e-2
+
+
+def rel_err(y, ref):
+    y, ref = y.float().cpu(), ref.float().cpu()
+    return ((y - ref).abs().max() / ref.abs().max().clamp_min(1e-12)).item()
+
+
+class Setup:
+    def __init__(self, geo, C, r, dev, tmp_path):
+        self.geo, self.C, self.r, self.dev = geo, C, r, dev
+        ref_model = owhisper.build_whisper(geo)
+        self.cfg = ref_model.config
+        self.weights = owhisper.make_adapter_weights(ref_model, r, C)
+        sd = fixtures.make_router_state_dict(self.cfg.d_model, C)
+        self.oracle = owhisper.RoutedWhisperOracle(ref_model, self.weights, r, 2 * r, sd)
+        protos = owhisper.make_input_features(C, self.cfg.num_mel_bins, list(range(C)), C, seed=99)
+        self.oracle.router_sd = owhisper.fit_router_head(sd, self.oracle.lid_features(protos))
+        self.languages = [f"lang{k}" for k in range(C)]
+        self.paths = {}
+        for k, lang in enumerate(self.languages):     # adapters reach the product through PEFT's on-disk layout
+            owhisper.write_peft_adapter(tmp_path / lang, self.weights, k, r, 2 * r)
+            self.paths[lang] = tmp_path / lang
+        gpu_model = owhisper.build_whisper(geo).to(torch.bfloat16).to(dev)
+        clf = sar.LanguageClassifier(input_dim=self.cfg.d_model, num_classes=C, languages=self.languages)
+        clf.load_state_dict(self.oracle.router_sd)
+        self.router = sar.AdapterRouter(gpu_model, self.paths, clf.eval().to(dev), self.languages).eval()
+
+    def batch(self, B, T_dec, kind="uniform", seed=0):
+        langs = fixtures.language_mix(B, self.C, kind, seed=7 + seed)
+        x = owhisper.make_input_features(B, self.cfg.num_mel_bins, langs, self.C, seed=2234 + seed)
+        dec, labels = owhisper.make_decoder_inputs(B, T_dec, self.cfg.vocab_size, self.cfg.decoder_start_token_id)
+        return x, dec, labels, langs
+
+
+@pytest.fixture(scope="module")
+def micro(cuda_dev, tmp_path_factory):
+    return Setup("micro", 4, 16, cuda_dev, tmp_path_factory.mktemp("micro"))
+
+
+@pytest.fixture(scope="module")
+def tiny(cuda_dev, tmp_path_factory):
+    return Setup("tiny", 4, 16, cuda_dev, tmp_path_factory.mktemp("tiny"))
+
+
+@pytest.mark.parametrize("kind", ["uniform", "skewed", "single"])
+def test_router_indices_bit_exact_and_logits_within_tolerance(micro, kind):
+    s = micro
+    x, dec, labels, langs = s.batch(8, 12, kind)
+    ref = s.oracle.forward_hard(x, dec, labels, capture=True)
+    xg = x.to(s.dev).to(torch.bfloat16)
+    captured = {}
+    hooks = [m.register_forward_hook(lambda mod, inp, out, p=p: captured.setdefault(p, []).append(out.detach()))
+             for p, m in sar.lora_modules(s.router.whisper).items()]
+    try:
+        with torch.no_grad():
+            h = s.router.extract_encoder_features(xg)
+            routed = s.router.detect_indices(h)
+            captured.clear()            # keep only the routed pass (the LID pass runs the same modules on base weights)
+            out = s.router._hard_routing(xg, routed.idx, labels.to(s.dev))
+    finally:
+        for hk in hooks:
+            hk.remove()
+    assert torch.equal(routed.idx.cpu().long(), ref["idx"])                       # bit-exact routing
+    assert ref["idx"].tolist() == langs                                           # and it is the intended mix
+    for p, want in ref["captured"].items():                                       # every LoRA'd module, both stacks
+        assert rel_err(captured[p][0], want) <= MODULE_TOL, p
+    assert rel_err(out["logits"], ref["logits"]) <= LOGIT_TOL
+    assert abs(out["loss"].item() - ref["loss"].item()) <= 2e-2 * abs(ref["loss"].item())
+    assert out["logits"].shape == ref["logits"].shape
+
+
+def test_forward_public_api_and_language_names(micro):
+    s = micro
+    x, dec, labels, langs = s.batch(6, 10, seed=1)
+    xg = x.to(s.dev).to(torch.bfloat16)
+    with torch.no_grad():
+        out = s.router(xg, labels=labels.to(s.dev))
+        names, probs = s.router.detect_language(s.router.extract_encoder_features(xg))
+    assert set(out) == {"loss", "logits"}
+    assert names == [s.languages[k] for k in langs]
+    assert probs.shape == (6, s.C) and torch.allclose(probs.sum(-1).cpu(), torch.ones(6), atol=1e-5)
+    ref = s.oracle.forward_hard(x, dec, labels)
+    assert rel_err(out["logits"], ref["logits"]) <= LOGIT_TOL
+
+
+def test_lid_features_come_from_base_weights(micro):
+    """The LID pass must not see any adapter: features equal those of the un-adapted oracle encoder."""
+    s = micro
+    x, *_ = s.batch(4, 4, seed=2)
+    h = s.router.extract_encoder_features(x.to(s.dev).to(torch.bfloat16))
+    assert rel_err(h, s.oracle.lid_features(x)) <= MODULE_TOL
+
+
+def test_tiny_geometry_end_to_end(tiny):
+    s = tiny
+    x, dec, labels, langs = s.batch(5, 16, "uniform", seed=3)
+    ref = s.oracle.forward_hard(x, dec, labels)
+    with torch.no_grad():
+        xg = x.to(s.dev).to(torch.bfloat16)
+        routed = s.router.detect_indices(s.router.extract_encoder_features(xg))
+        out = s.router(xg, labels=labels.to(s.dev))
+    assert torch.equal(routed.idx.cpu().long(), ref["idx"])
+    assert rel_err(out["logits"], ref["logits"]) <= LOGIT_TOL
+
+
+def test_soft_routing_matches_reference_semantics(micro):
+    """Soft strategy = every adapter on the whole batch, logits mixed by LID probability (reference :627-670)."""
+    s = micro
+    x, dec, labels, _ = s.batch(4, 8, seed=4)
+    _, rout, _ = s.oracle.detect(x)
+    probs = rout["probs"]
+    want = None
+    for k in range(s.C):
+        r = s.oracle.forward_hard(x, dec, idx=torch.full((4,), k))
+        term = probs[:, k, None, None] * r["logits"]
+        want = term if want is None else want + term
+    s.router.strategy = "soft"
+    try:
+        with torch.no_grad():
+            out = s.router(x.to(s.dev).to(torch.bfloat16), decoder_input_ids=dec.to(s.dev))
+    finally:
+        s.router.strategy = "hard"
+    assert set(out) == {"loss", "logits", "probs"}
+    assert rel_err(out["logits"], want) <= LOGIT_TOL
+
+
+def test_greedy_generation_matches_oracle_tokens(micro):
+    """Identical greedy token sequences; a sequence is compared up to (excluding) the first step whose oracle
+    top-1/top-2 logit margin is below the bf16 noise floor, where argmax is legitimately ambiguous."""
+    s = micro
+    B, steps = 6, 8
+    x, *_ = s.batch(B, 4, seed=5)
+    want = s.oracle.generate_hard(x, max_new_tokens=steps)
+    with torch.no_grad():
+        got = s.router.generate(x.to(s.dev).to(torch.bfloat16), max_new_tokens=steps, num_beams=1, do_sample=False)
+    got = got.cpu()
+    assert got.shape[0] == B
+    # oracle margins per generated position, teacher-forced on the oracle's own tokens
+    idx, _, _ = s.oracle.detect(x)
+    full = 0
+    for i in range(B):
+        L = min(want.shape[1], got.shape[1])
+        seq = want[i:i + 1, :L]
+        start = torch.full((1, 1), s.cfg.decoder_start_token_id)
+        dec_in = torch.cat([start, seq[:, :-1]], 1) if seq[0, 0] != s.cfg.decoder_start_token_id else seq
+        r = s.oracle.forward_hard(x[i:i + 1], dec_in, idx=idx[i:i + 1])
+        margins = orouter.top2_margin(r["logits"][0])
+        n_ok = L
+        low = (margins < 2e-2).nonzero()
+        if len(low):
+            n_ok = int(low[0])
+        assert torch.equal(got[i, :n_ok], want[i, :n_ok]), (i, got[i].tolist(), want[i].tolist())
+        full += int(torch.equal(got[i, :L], want[i, :L]))
+    assert full >= B - 2
+
+
+def test_module_default_and_beam_expanded_routing(cuda_dev):
+    """RoutedLoRALinear outside any routing context uses its active adapter (plain WhisperLoRA behaviour); inside a
+    context with fewer utterances than batch rows (beam search) the index is expanded."""
+    dev = cuda_dev
+    c = fixtures.make_lora_case(4, 50, 256, 256, 16, 3)
+    lin = torch.nn.Linear(256, 256).to(dev).to(torch.bfloat16)
+    with torch.no_grad():
+        lin.weight.copy_(c.W)
+        lin.bias.copy_(c.bias)
+    m = sar.RoutedLoRALinear(lin, None)
+    for k in range(3):
+        m.add_adapter(f"a{k}", 16, 32)
+        with torch.no_grad():
+            m.lora_A[f"a{k}"].weight.copy_(c.A_stack[k])
+            m.lora_B[f"a{k}"].weight.copy_(c.B_stack[k])
+    m.eval()
+    m.set_adapter("a2")
+    x = c.x.to(dev)
+    with torch.no_grad():
+        y = m(x)
+        ref = olora.lora_linear_routed_k1_rounding(c.x, c.W, c.bias, c.A_stack, c.B_stack, 2.0,
+                                                   torch.full((4,), 2, dtype=torch.int32))
+        assert rel_err(y, ref) <= 2 ** -7
+        with sar.route(torch.tensor([0, 1], device=dev)):          # 2 utterances x 2 beams
+            yb = m(x)
+        refb = olora.lora_linear_routed_k1_rounding(c.x, c.W, c.bias, c.A_stack, c.B_stack, 2.0,
+                                                    torch.tensor([0, 0, 1, 1], dtype=torch.int32))
+        assert rel_err(yb, refb) <= 2 ** -7
+        m.disable_adapters = True
+        assert rel_err(m(x), torch.nn.functional.linear(c.x.float(), c.W.float(), c.bias.float())) <= 2 ** -7
+        m.disable_adapters = False
+        assert m(x.float()).dtype == torch.float32                  # output follows the input dtype
+        with sar.route(torch.tensor([0, 1, 2], device=dev)), pytest.raises(ValueError):
+            m(x)
+
+
+def test_whisper_lora_training_step_grads_match_oracle(cuda_dev, monkeypatch):
+    """BASELINE config 5 shape family (single adapter, fwd + LoRA-only bwd): gradients of every lora_A / lora_B from
+    K3 through autograd equal fp32 autograd of the oracle model on the same batch."""
+    monkeypatch.setenv("SAR_RANDOM_INIT", "1")
+    dev = cuda_dev
+    w = sar.WhisperLoRA("whisper-tiny", lora_r=16, lora_alpha=32, lora_dropout=0.0, device="cuda",
+                        use_gradient_checkpointing=False)
+    cfg = w.model.config
+    hf = w.model.base_model.model
+    # fp32 oracle copy with identical base weights (bf16 values) and identical adapter weights
+    ref_model = owhisper.build_whisper("tiny")
+    ref_model.load_state_dict({k: v.float().cpu() for k, v in hf.state_dict().items()
+                               if ".lora_" not in k and ".base_layer." not in k}, strict=False)
+    weights = owhisper.make_adapter_weights(ref_model, 16, 1)
+    for p, m in sar.lora_modules(hf).items():
+        ref_lin = ref_model.get_submodule(p)
+        with torch.no_grad():
+            ref_lin.weight.copy_(m.base_layer.weight.float().cpu())
+            ref_lin.bias.copy_(m.base_layer.bias.float().cpu())
+            m.lora_A["default"].weight.copy_(weights[p][0][0])
+            m.lora_B["default"].weight.copy_(weights[p][1][0])
+    params = {}
+    for p, (A, B) in weights.items():
+        params[p] = (A[0].clone().requires_grad_(True), B[0].clone().requires_grad_(True))
+        lin = ref_model.get_submodule(p)
+
+        def fwd(x, lin=lin, A=params[p][0], B=params[p][1]):
+            return olora.lora_linear(x, lin.weight, lin.bias, A, B, 2.0)
+        lin.forward = fwd
+    B_, T_dec = 2, 6
+    x = owhisper.make_input_features(B_, cfg.num_mel_bins, [0, 0], 1, seed=8)
+    dec, labels = owhisper.make_decoder_inputs(B_, T_dec, cfg.vocab_size, cfg.decoder_start_token_id)
+    ref_model.train(False)
+    ref_loss = ref_model(input_features=x, labels=labels).loss
+    ref_loss.backward()
+
+    w.train()
+    out = w(input_features=x.to(dev).to(torch.bfloat16), labels=labels.to(dev))
+    out.loss.backward()
+    assert abs(out.loss.item() - ref_loss.item()) <= 2e-2 * abs(ref_loss.item())
+    checked = 0
+    for p, m in sar.lora_modules(hf).items():
+        gA, gB = m.lora_A["default"].weight.grad, m.lora_B["default"].weight.grad
+        assert gA is not None and gB is not None and gA.dtype == torch.float32
+        rA, rB = params[p][0].grad, params[p][1].grad
+        # layer-wise gradients shrink with depth; compare against the largest gradient of the same kind
+        assert rel_err(gA, rA) <= 8e-2, p
+        assert rel_err(gB, rB) <= 8e-2, p
+        checked += 1
+    assert checked == 6 * cfg.encoder_layers
+    assert all(p.grad is None for n, p in w.model.named_parameters() if ".lora_" not in n)
+
+
+def test_save_and_reload_adapter_on_gpu(cuda_dev, tmp_path, monkeypatch):
+    monkeypatch.setenv("SAR_RANDOM_INIT", "1")
+    w = sar.WhisperLoRA("whisper-tiny", lora_r=16, lora_alpha=32, lora_dropout=0.0, device="cuda")
+    with torch.no_grad():
+        for m in sar.lora_modules(w.model).values():
+            m.lora_B["default"].weight.normal_(0, 0.02)
+    cfg = w.model.config
+    x = owhisper.make_input_features(2, cfg.num_mel_bins, [0, 0], 1, seed=9).to("cuda").to(torch.bfloat16)
+    dec, _ = owhisper.make_decoder_inputs(2, 5, cfg.vocab_size, cfg.decoder_start_token_id)
+    w.eval()
+    with torch.no_grad():
+        a = w(input_features=x, decoder_input_ids=dec.to("cuda")).logits
+    w.save_adapter(tmp_path / "final")
+    w2 = sar.load_whisper_lora_from_checkpoint(tmp_path / "final", "whisper-tiny", device="cuda")
+    w2.eval()
+    with torch.no_grad():
+        b = w2(input_features=x, decoder_input_ids=dec.to("cuda")).logits
+    assert torch.equal(a, b)
+    ids = w2.generate(x, max_new_tokens=4)
+    assert ids.shape[0] == 2
