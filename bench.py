@@ -280,11 +280,13 @@ def run_b200_arm(args):
     ops.K1_TIMELINE = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_wall0 = time.time()
+    torch.cuda.nvtx.range_push("timed")
     e0.record()
     for i in range(args.steps):
         out = step(dev_inputs[i % n_in])
     e1.record()
     barrier()
+    torch.cuda.nvtx.range_pop()
     t_wall1 = time.time()
     clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
     timeline, ops.K1_TIMELINE = ops.K1_TIMELINE, None

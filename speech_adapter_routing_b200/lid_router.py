@@ -378,7 +378,9 @@ class AdapterRouter(nn.Module):
         kw = {k: v for k, v in kwargs.items()
               if k in ("attention_mask", "decoder_input_ids", "decoder_attention_mask")}
         with route(utt_adapter):
-            return self.whisper(input_features=input_features, labels=labels, **kw)
+            # AdapterRouter.forward returns only loss / logits, so no KV cache is built (HF would otherwise
+            # torch.cat every layer's K/V into a DynamicCache: 48 extra full-size copies per whisper-small step)
+            return self.whisper(input_features=input_features, labels=labels, use_cache=False, **kw)
 
     def forward(self, input_features: torch.Tensor, labels: Optional[torch.Tensor] = None,
                 **kwargs) -> Dict[str, torch.Tensor]:
