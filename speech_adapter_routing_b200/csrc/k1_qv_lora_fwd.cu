@@ -418,6 +418,11 @@ int k1_qv_lora_fwd(const K1Args& a, cudaStream_t stream) {
   int bn = a.block_n_override;
   if (bn == 0) bn = (a.d_out % 192 == 0) ? 192 : (a.d_out % 128 == 0) ? 128 : 64;
   if (a.d_out % bn) return fail(SAR_EINVAL, "k1: d_out not divisible by BLOCK_N");
+  // CTA-pair kernel (cta_group::2, 256-row units) whenever an utterance has more than one 128-row tile; the
+  // single-CTA kernel keeps short sequences (decoder T_dec <= 128, decode steps) from wasting half a pair.
+  const bool pair_ok = (bn == 128 || bn == 192);
+  const bool want_pair = a.kernel_override == 2 || (a.kernel_override == 0 && a.T > 128);
+  if (pair_ok && want_pair) return k1v2_qv_lora_fwd(a, bn, stream);
   switch (bn) {
     case 64: return k1_launch<64>(a, stream);
     case 128: return k1_launch<128>(a, stream);

@@ -1,0 +1,460 @@
+// k1_qv_lora_fwd_2cta.cu — K1 v2: the fused q/v GEMM + routed LoRA epilogue on CTA PAIRS (tcgen05 cta_group::2).
+//
+// Same math and same per-unit structure as k1_qv_lora_fwd.cu (see the design notes there), re-tiled so that one
+// tcgen05.mma spans two SMs: a pair owns 256 rows of ONE utterance (128 per CTA) and every B operand (W tile, A_k
+// tile, B_k tile) is split in halves between the two CTAs, which halves the per-SM operand ingest from L2 — the
+// limiter of the single-CTA kernel (ncu: tensor pipe 50 % active at 104 B/clk/SM demanded vs ~64 B/clk/SM served).
+//
+// Scheduling: work is the flat list of (unit, N-tile) steps; pair p owns a contiguous, balanced range of it, so
+// the last wave is never more than one tile-step long.  A range that starts in the middle of a unit first runs a
+// U-only pass (loads X and A_k, issues only the N=r MMAs) to rebuild the low-rank intermediate of that unit.
+//
+// Roles per CTA (192 threads): warp 0 TMA producer (both CTAs load their halves; completion bytes are signalled on
+// the LEADER's mbarriers), warp 1 TMEM alloc + (leader only) single-thread MMA issue with multicast commits,
+// warps 2-5 epilogue on the CTA's own 128 TMEM lanes.
+#include "sar_internal.h"
+#include "sar_ptx.cuh"
+
+namespace sar {
+
+constexpr int V2_ROWS_PER_CTA = 128;
+constexpr int V2_BLOCK_K = 64;
+constexpr int V2_THREADS = 192;
+constexpr int V2_X_BYTES = V2_ROWS_PER_CTA * V2_BLOCK_K * 2;  // 16 KB
+constexpr int V2_U_BYTES = V2_ROWS_PER_CTA * 128;             // 16 KB
+constexpr int V2_STG_BYTES = 32 * 128;
+constexpr int V2_MAX_STAGES = 8;
+
+struct K1V2Params {
+  int B, T, d_in, d_out, r;
+  int tiles_per_utt;   // 256-row tiles per utterance
+  int n_tiles, k_blocks, num_stages, n_adapters;
+  long long total_steps;  // num_units * n_tiles
+  int num_pairs;
+  int swap_halves;     // debug: which CTA of the pair supplies the upper half of every B operand
+  float scale;
+  const int32_t* utt_adapter;
+  const __nv_bfloat16* bias;
+  __nv_bfloat16* u_out;
+};
+
+template <int BLOCK_N>
+struct V2Smem {
+  static constexpr int WH_BYTES = (BLOCK_N / 2) * 128;
+  static constexpr int BPH_BYTES = (BLOCK_N / 2) * 128;
+  static __host__ __device__ int ah_bytes(int r) { return (r / 2) * 128; }                      // bytes TMA writes
+  static __host__ __device__ int ah_slot(int r) { return ((r / 2) * 128 + 1023) & ~1023; }      // 1 KB-aligned slot
+  static __host__ __device__ int stage_bytes(int r) { return V2_X_BYTES + WH_BYTES + ah_slot(r); }
+  static __host__ __device__ int fixed_bytes() { return V2_U_BYTES + BPH_BYTES + 4 * 2 * V2_STG_BYTES + 512; }
+};
+
+template <int BLOCK_N>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V2_THREADS, 1)
+k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
+            const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+            const __grid_constant__ CUtensorMap tm_y, const K1V2Params p) {
+  using L = V2Smem<BLOCK_N>;
+  constexpr int TMEM_COLS = 512;
+  constexpr int U_COL = 2 * BLOCK_N;
+  static_assert(2 * BLOCK_N + 64 <= TMEM_COLS, "TMEM budget");
+  static_assert(BLOCK_N % 64 == 0 && BLOCK_N <= 256, "BLOCK_N");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int S = p.num_stages;
+  const int stage_bytes = L::stage_bytes(p.r);
+  uint8_t* stages = smem;
+  uint8_t* u_tile = stages + S * stage_bytes;
+  uint8_t* bp_tile = u_tile + V2_U_BYTES;
+  uint8_t* stg = bp_tile + L::BPH_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg + 4 * 2 * V2_STG_BYTES);
+  uint64_t* full = bars;                          // [S]  leader only (count 1 + tx of BOTH CTAs)
+  uint64_t* empty = bars + V2_MAX_STAGES;         // [S]  per CTA (count 1, multicast commit)
+  uint64_t* tmem_full = bars + 2 * V2_MAX_STAGES; // [2]  per CTA (multicast commit)
+  uint64_t* tmem_empty = tmem_full + 2;           // [2]  leader only (count 8: 4 epilogue warps x 2 CTAs)
+  uint64_t* u_full = tmem_empty + 2;              //      per CTA (multicast commit)
+  uint64_t* u_ready = u_full + 1;                 //      leader only (count 8)
+  uint64_t* b_full = u_ready + 1;                 //      leader only (count 1 + tx of both)
+  uint64_t* b_empty = b_full + 1;                 //      per CTA (multicast commit)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_empty + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1;
+  const bool has_lora = (p.n_adapters > 0) && (p.utt_adapter != nullptr);
+  const uint32_t half = p.swap_halves ? (rank ^ 1u) : rank;   // which half of every B operand this CTA supplies
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm_x);
+    tma_prefetch_desc(&tm_w);
+    tma_prefetch_desc(&tm_y);
+    if (has_lora) {
+      tma_prefetch_desc(&tm_a);
+      tma_prefetch_desc(&tm_b);
+    }
+    for (int s = 0; s < S; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tmem_full[i], 1);
+      mbar_init(&tmem_empty[i], 8);
+    }
+    mbar_init(u_full, 1);
+    mbar_init(u_ready, 8);
+    mbar_init(b_full, 1);
+    mbar_init(b_empty, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) {
+    tmem_alloc_2sm(tmem_ptr, TMEM_COLS);
+    tmem_relinquish_2sm();
+  }
+  tc_fence_before();
+  cluster_sync_all();   // barrier inits + TMEM allocation of BOTH CTAs are visible before any cross-CTA traffic
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int KB = p.k_blocks;
+  const int NT = p.n_tiles;
+  const int bp_issue_kb = KB > 2 ? KB / 2 : 0;
+  const long long g0 = p.total_steps * pair / p.num_pairs;
+  const long long g1 = p.total_steps * (pair + 1) / p.num_pairs;
+
+  // leader-side barrier addresses as seen from this CTA (shared::cluster window of rank 0)
+  auto leader_addr = [&](uint64_t* bar) { return mapa_u32(smem_u32(bar), 0); };
+
+  if (warp == 0) {
+    // =============================================================== TMA producer (both CTAs)
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t b_uses = 0;
+      const uint32_t b_full_leader = leader_addr(b_full);
+      auto k_loop = [&](int b, int m0, int k, int n0, bool main, bool with_a, bool with_bp) {
+        const uint32_t tx_cta = V2_X_BYTES + (main ? L::WH_BYTES : 0) + (with_a ? L::ah_bytes(p.r) : 0);
+        for (int kb = 0; kb < KB; ++kb) {
+          if (with_bp && kb == bp_issue_kb) {
+            mbar_wait(b_empty, (b_uses & 1) ^ 1);
+            if (leader) mbar_arrive_expect_tx(b_full, 2 * L::BPH_BYTES);
+            tma_load_2d_2sm(bp_tile, &tm_b, b_full_leader, 0, k * p.d_out + n0 + half * (BLOCK_N / 2));
+            ++b_uses;
+          }
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* st = stages + stage * stage_bytes;
+          const uint32_t full_leader = leader_addr(&full[stage]);
+          if (leader) mbar_arrive_expect_tx(&full[stage], 2 * tx_cta);
+          tma_load_3d_2sm(st, &tm_x, full_leader, kb * V2_BLOCK_K, m0, b);
+          if (main) tma_load_2d_2sm(st + V2_X_BYTES, &tm_w, full_leader, kb * V2_BLOCK_K, n0 + half * (BLOCK_N / 2));
+          if (with_a)
+            tma_load_2d_2sm(st + V2_X_BYTES + L::WH_BYTES, &tm_a, full_leader, kb * V2_BLOCK_K,
+                            k * p.r + half * (p.r / 2));
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      };
+      long long g = g0;
+      while (g < g1) {
+        const int unit = static_cast<int>(g / NT);
+        const int nt_first = static_cast<int>(g - static_cast<long long>(unit) * NT);
+        const int nt_last = static_cast<int>(min(static_cast<long long>(NT), nt_first + (g1 - g)));
+        const int b = unit / p.tiles_per_utt;
+        const int m0 = (unit - b * p.tiles_per_utt) * 256 + rank * V2_ROWS_PER_CTA;
+        int k = has_lora ? p.utt_adapter[b] : -1;
+        if (k < 0 || k >= p.n_adapters) k = -1;
+        if (k >= 0 && nt_first > 0) k_loop(b, m0, k, 0, false, true, false);   // U-only pass
+        for (int nt = nt_first; nt < nt_last; ++nt) k_loop(b, m0, k, nt * BLOCK_N, true, k >= 0 && nt == 0, k >= 0);
+        g += nt_last - nt_first;
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // =============================================================== MMA issuer (leader CTA, single thread)
+    if (leader && lane == 0) {
+      const uint32_t idesc_main = umma_idesc_bf16(256, BLOCK_N);
+      const uint32_t idesc_u = umma_idesc_bf16(256, p.r);
+      const uint32_t u_desc_base = smem_u32(u_tile);
+      const uint32_t bp_desc_base = smem_u32(bp_tile);
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t tile_iter = 0, lora_units = 0, b_uses = 0;
+      auto k_loop = [&](uint32_t acc, bool main, bool with_a) {
+        for (int kb = 0; kb < KB; ++kb) {
+          mbar_wait(&full[stage], phase);
+          tc_fence_after();
+          const uint32_t st = smem_u32(stages + stage * stage_bytes);
+          const uint64_t xd = umma_desc_sw128(st);
+          if (main) {
+            const uint64_t wd = umma_desc_sw128(st + V2_X_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < V2_BLOCK_K / 16; ++kk)
+              umma_bf16_2sm(acc, xd + 2 * kk, wd + 2 * kk, idesc_main, (kb | kk) != 0);
+          }
+          if (with_a) {
+            const uint64_t ad = umma_desc_sw128(st + V2_X_BYTES + L::WH_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < V2_BLOCK_K / 16; ++kk)
+              umma_bf16_2sm(tmem_base + U_COL, xd + 2 * kk, ad + 2 * kk, idesc_u, (kb | kk) != 0);
+          }
+          umma_commit_2sm(&empty[stage], 0b11);
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1;
+          }
+        }
+      };
+      auto publish_u = [&]() {   // U accumulator complete -> both CTAs' epilogue warps convert their rows
+        umma_commit_2sm(u_full, 0b11);
+        mbar_wait(u_ready, lora_units & 1);
+        tc_fence_after();
+        ++lora_units;
+      };
+      long long g = g0;
+      while (g < g1) {
+        const int unit = static_cast<int>(g / NT);
+        const int nt_first = static_cast<int>(g - static_cast<long long>(unit) * NT);
+        const int nt_last = static_cast<int>(min(static_cast<long long>(NT), nt_first + (g1 - g)));
+        const int b = unit / p.tiles_per_utt;
+        int k = has_lora ? p.utt_adapter[b] : -1;
+        if (k < 0 || k >= p.n_adapters) k = -1;
+        if (k >= 0 && nt_first > 0) {
+          k_loop(0, false, true);
+          publish_u();
+        }
+        for (int nt = nt_first; nt < nt_last; ++nt, ++tile_iter) {
+          const uint32_t buf = tile_iter & 1;
+          const uint32_t acc = tmem_base + buf * BLOCK_N;
+          mbar_wait(&tmem_empty[buf], ((tile_iter >> 1) & 1) ^ 1);
+          tc_fence_after();
+          k_loop(acc, true, k >= 0 && nt == 0);
+          if (k >= 0) {
+            if (nt == 0) publish_u();
+            mbar_wait(b_full, b_uses & 1);
+            tc_fence_after();
+            const uint64_t ud = umma_desc_sw128(u_desc_base);
+            const uint64_t bd = umma_desc_sw128(bp_desc_base);
+            const int ksteps = p.r >> 4;
+            for (int kk = 0; kk < ksteps; ++kk) umma_bf16_2sm(acc, ud + 2 * kk, bd + 2 * kk, idesc_main, 1u);
+            umma_commit_2sm(b_empty, 0b11);
+            ++b_uses;
+          }
+          umma_commit_2sm(&tmem_full[buf], 0b11);
+        }
+        g += nt_last - nt_first;
+      }
+    }
+    __syncwarp();
+  } else {
+    // =============================================================== epilogue warps (2..5), both CTAs
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
+    uint8_t* my_stg = stg + q * (2 * V2_STG_BYTES);
+    const uint32_t sw = static_cast<uint32_t>(lane & 7);
+    uint32_t tile_iter = 0, lora_units = 0, stg_idx = 0;
+    const uint32_t u_ready_leader = leader_addr(u_ready);
+    const uint32_t tmem_empty_leader[2] = {leader_addr(&tmem_empty[0]), leader_addr(&tmem_empty[1])};
+    long long g = g0;
+    while (g < g1) {
+      const int unit = static_cast<int>(g / NT);
+      const int nt_first = static_cast<int>(g - static_cast<long long>(unit) * NT);
+      const int nt_last = static_cast<int>(min(static_cast<long long>(NT), nt_first + (g1 - g)));
+      const int b = unit / p.tiles_per_utt;
+      const int m0 = (unit - b * p.tiles_per_utt) * 256 + rank * V2_ROWS_PER_CTA;
+      int k = has_lora ? p.utt_adapter[b] : -1;
+      if (k < 0 || k >= p.n_adapters) k = -1;
+      if (k >= 0) {
+        // ---- U: TMEM fp32 -> scale -> bf16 -> swizzled smem A-operand tile of THIS CTA (+ optional global save)
+        mbar_wait(u_full, lora_units & 1);
+        tc_fence_after();
+        const uint32_t u_row = smem_u32(u_tile) + row * 128;
+        // the unit's rows are saved exactly once: by the range that owns its N-tile 0
+        const bool save = (p.u_out != nullptr) && (nt_first == 0) && (m0 + row < p.T);
+        uint4* u_dst = save ? reinterpret_cast<uint4*>(p.u_out + (static_cast<size_t>(b) * p.T + m0 + row) * p.r)
+                            : nullptr;
+        for (int j = 0; j < (p.r >> 4); ++j) {
+          uint32_t v[16];
+          tmem_ld_32x16(tmem_base + lane_addr + U_COL + j * 16, v);
+          tmem_ld_wait();
+          uint32_t pk[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            pk[i] = pack_bf16x2(__uint_as_float(v[2 * i]) * p.scale, __uint_as_float(v[2 * i + 1]) * p.scale);
+          st_shared_v4(u_row + (((2 * j) ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
+          st_shared_v4(u_row + (((2 * j + 1) ^ sw) << 4), pk[4], pk[5], pk[6], pk[7]);
+          if (save) {
+            u_dst[2 * j] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+            u_dst[2 * j + 1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+          }
+        }
+        tc_fence_before();
+        asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy smem writes -> async proxy (peer-issued UMMA)
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(u_ready_leader);
+        ++lora_units;
+      }
+      for (int nt = nt_first; nt < nt_last; ++nt, ++tile_iter) {
+        const uint32_t buf = tile_iter & 1;
+        const int n0 = nt * BLOCK_N;
+        mbar_wait(&tmem_full[buf], (tile_iter >> 1) & 1);
+        tc_fence_after();
+        const bool rows_live = (m0 + q * 32) < p.T;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N / 64; ++c) {
+          uint32_t v0[32], v1[32];
+          const uint32_t taddr = tmem_base + lane_addr + buf * BLOCK_N + c * 64;
+          tmem_ld_32x32(taddr, v0);
+          tmem_ld_32x32(taddr + 32, v1);
+          if (lane == 0) tma_store_wait_read<1>();
+          __syncwarp();
+          tmem_ld_wait();
+          uint8_t* sbuf = my_stg + (stg_idx & 1) * V2_STG_BYTES;
+          const uint32_t srow = smem_u32(sbuf) + lane * 128;
+          const uint4* bias4 = p.bias ? reinterpret_cast<const uint4*>(p.bias + n0 + c * 64) : nullptr;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float bf[8];
+            if (bias4) {
+              const uint4 bb = __ldg(bias4 + j);
+              const uint32_t w[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                bf[2 * i] = __uint_as_float(w[i] << 16);
+                bf[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) bf[i] = 0.f;
+            }
+            uint32_t pk[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int e = 8 * j + 2 * i;
+              const float a0 = __uint_as_float(e < 32 ? v0[e & 31] : v1[e & 31]);
+              const float a1 = __uint_as_float(e < 32 ? v0[(e + 1) & 31] : v1[(e + 1) & 31]);
+              pk[i] = pack_bf16x2(a0 + bf[2 * i], a1 + bf[2 * i + 1]);
+            }
+            st_shared_v4(srow + ((static_cast<uint32_t>(j) ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
+          }
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0 && rows_live) {
+            tma_store_3d(&tm_y, sbuf, n0 + c * 64, m0 + q * 32, b);
+            tma_store_commit();
+          }
+          ++stg_idx;
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tmem_empty_leader[buf]);
+      }
+      g += nt_last - nt_first;
+    }
+    if (lane == 0) tma_store_wait_all<0>();
+    __syncwarp();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();   // neither CTA may free TMEM / exit while its peer still reads its smem or signals its barriers
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+template <int BLOCK_N>
+static int k1v2_launch(const K1Args& a, cudaStream_t stream) {
+  using L = V2Smem<BLOCK_N>;
+  const DeviceInfo& dev = device_info();
+  const bool has_lora = a.n_adapters > 0 && a.utt_adapter != nullptr && a.A_stack != nullptr && a.Bp_stack != nullptr;
+
+  K1V2Params p{};
+  p.B = a.B; p.T = a.T; p.d_in = a.d_in; p.d_out = a.d_out; p.r = has_lora ? a.r : 16;
+  p.tiles_per_utt = (a.T + 255) / 256;
+  p.n_tiles = a.d_out / BLOCK_N;
+  p.k_blocks = a.d_in / V2_BLOCK_K;
+  p.n_adapters = has_lora ? a.n_adapters : 0;
+  p.total_steps = static_cast<long long>(a.B) * p.tiles_per_utt * p.n_tiles;
+  p.scale = a.scale;
+  p.swap_halves = a.swap_halves;
+  p.utt_adapter = has_lora ? a.utt_adapter : nullptr;
+  p.bias = reinterpret_cast<const __nv_bfloat16*>(a.bias);
+  p.u_out = has_lora ? reinterpret_cast<__nv_bfloat16*>(a.u_out) : nullptr;
+
+  const int stage_bytes = L::stage_bytes(p.r);
+  const int budget = dev.max_smem_optin - 1024 - L::fixed_bytes();
+  int S = budget / stage_bytes;
+  if (S > V2_MAX_STAGES) S = V2_MAX_STAGES;
+  if (S < 2) return fail(SAR_EINVAL, "k1v2: shared memory budget too small for this shape");
+  p.num_stages = S;
+  const int smem_bytes = 1024 + S * stage_bytes + L::fixed_bytes();
+
+  int pairs = dev.num_sms / 2;
+  if (p.total_steps < pairs) pairs = static_cast<int>(p.total_steps);
+  if (a.grid_override > 0 && a.grid_override / 2 >= 1 && a.grid_override / 2 < pairs) pairs = a.grid_override / 2;
+  p.num_pairs = pairs;
+
+  CUtensorMap tm_x, tm_w, tm_a, tm_b, tm_y;
+  memset(&tm_a, 0, sizeof(tm_a));
+  memset(&tm_b, 0, sizeof(tm_b));
+  int rc;
+  {
+    const uint64_t dims[3] = {(uint64_t)a.d_in, (uint64_t)a.T, (uint64_t)a.B};
+    const uint64_t strides[2] = {(uint64_t)a.d_in * 2, (uint64_t)a.T * a.d_in * 2};
+    const uint32_t box[3] = {V2_BLOCK_K, V2_ROWS_PER_CTA, 1};
+    if ((rc = make_tmap_bf16(&tm_x, a.x, 3, dims, strides, box))) return rc;
+  }
+  {
+    const uint64_t dims[3] = {(uint64_t)a.d_out, (uint64_t)a.T, (uint64_t)a.B};
+    const uint64_t strides[2] = {(uint64_t)a.d_out * 2, (uint64_t)a.T * a.d_out * 2};
+    const uint32_t box[3] = {64, 32, 1};
+    if ((rc = make_tmap_bf16(&tm_y, a.y, 3, dims, strides, box))) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)a.d_in, (uint64_t)a.d_out};
+    const uint64_t strides[1] = {(uint64_t)a.d_in * 2};
+    const uint32_t box[2] = {V2_BLOCK_K, BLOCK_N / 2};
+    if ((rc = make_tmap_bf16(&tm_w, a.W, 2, dims, strides, box))) return rc;
+  }
+  if (has_lora) {
+    {
+      const uint64_t dims[2] = {(uint64_t)a.d_in, (uint64_t)a.n_adapters * a.r};
+      const uint64_t strides[1] = {(uint64_t)a.d_in * 2};
+      const uint32_t box[2] = {V2_BLOCK_K, (uint32_t)a.r / 2};
+      if ((rc = make_tmap_bf16(&tm_a, a.A_stack, 2, dims, strides, box))) return rc;
+    }
+    {
+      const uint64_t dims[2] = {(uint64_t)SAR_RPAD, (uint64_t)a.n_adapters * a.d_out};
+      const uint64_t strides[1] = {(uint64_t)SAR_RPAD * 2};
+      const uint32_t box[2] = {64, BLOCK_N / 2};
+      if ((rc = make_tmap_bf16(&tm_b, a.Bp_stack, 2, dims, strides, box))) return rc;
+    }
+  }
+
+  auto kern = k1v2_kernel<BLOCK_N>;
+  static thread_local int smem_set = 0;
+  if (smem_set < smem_bytes) {
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.max_smem_optin);
+    if (e != cudaSuccess) return fail_cuda(e, "k1v2: cudaFuncSetAttribute");
+    smem_set = dev.max_smem_optin;
+  }
+  kern<<<2 * pairs, V2_THREADS, smem_bytes, stream>>>(tm_x, tm_w, tm_a, tm_b, tm_y, p);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail_cuda(e, "k1v2: launch");
+  return SAR_OK;
+}
+
+int k1v2_qv_lora_fwd(const K1Args& a, int block_n, cudaStream_t stream) {
+  switch (block_n) {
+    case 128: return k1v2_launch<128>(a, stream);
+    case 192: return k1v2_launch<192>(a, stream);
+    default: return fail(SAR_EINVAL, "k1v2: unsupported BLOCK_N");
+  }
+}
+
+}  // namespace sar

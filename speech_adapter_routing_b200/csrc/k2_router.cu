@@ -27,15 +27,18 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// Raw 8-element vector as loaded from HBM (converted to fp32 only when consumed, so the NEXT pair of frames can be
+// in flight in few registers while the current pair is being reduced).
 template <bool FP32>
-__device__ __forceinline__ void load8(const void* row, int elem, float (&out)[8]) {
-  if constexpr (FP32) {
-    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(row) + elem);
-    const float4 a = __ldg(p), b = __ldg(p + 1);
-    out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w;
-    out[4] = b.x; out[5] = b.y; out[6] = b.z; out[7] = b.w;
-  } else {
-    const uint4 v = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(row) + elem));
+struct Raw8;
+template <>
+struct Raw8<false> {
+  uint4 v;
+  __device__ __forceinline__ void load(const void* row, int elem) {
+    v = __ldg(reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(row) + elem));
+  }
+  __device__ __forceinline__ void zero() { v = make_uint4(0, 0, 0, 0); }
+  __device__ __forceinline__ void to_float(float (&out)[8]) const {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -43,7 +46,21 @@ __device__ __forceinline__ void load8(const void* row, int elem, float (&out)[8]
       out[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
     }
   }
-}
+};
+template <>
+struct Raw8<true> {
+  float4 a, b;
+  __device__ __forceinline__ void load(const void* row, int elem) {
+    const float4* p = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(row) + elem);
+    a = __ldg(p);
+    b = __ldg(p + 1);
+  }
+  __device__ __forceinline__ void zero() { a = b = make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ void to_float(float (&out)[8]) const {
+    out[0] = a.x; out[1] = a.y; out[2] = a.z; out[3] = a.w;
+    out[4] = b.x; out[5] = b.y; out[6] = b.z; out[7] = b.w;
+  }
+};
 
 // grid = (chunks, B); each CTA reduces `rows_per_chunk` frames of one utterance to a d-vector of
 // sum_t (x - mean_t) * rstd_t, written to partial[b][chunk][d].
@@ -67,23 +84,35 @@ k2_pool_kernel(const void* __restrict__ h, float* __restrict__ partial, int* __r
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[v][i] = 0.f;
 
-  for (int t = t0 + warp; t < t1; t += 2 * K2_WARPS) {
-    const int tb = t + K2_WARPS;
-    const bool has_b = tb < t1;
+  Raw8<FP32> na[NV], nb[NV];
+  auto issue = [&](int t) {  // loads of frames t and t + K2_WARPS (the second may not exist)
+    const bool has_b = (t + K2_WARPS) < t1;
     const uint8_t* ra = base + static_cast<size_t>(t) * d * esz;
-    const uint8_t* rb = base + static_cast<size_t>(has_b ? tb : t) * d * esz;
-    float xa[NV][8], xb[NV][8];
+    const uint8_t* rb = base + static_cast<size_t>(has_b ? t + K2_WARPS : t) * d * esz;
 #pragma unroll
     for (int v = 0; v < NV; ++v) {
       const int e = (v * 32 + lane) * 8;
       if (e < d) {
-        load8<FP32>(ra, e, xa[v]);
-        load8<FP32>(rb, e, xb[v]);
+        na[v].load(ra, e);
+        nb[v].load(rb, e);
       } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) xa[v][i] = xb[v][i] = 0.f;
+        na[v].zero();
+        nb[v].zero();
       }
     }
+  };
+
+  int t = t0 + warp;
+  if (t < t1) issue(t);
+  for (; t < t1; t += 2 * K2_WARPS) {
+    const bool has_b = (t + K2_WARPS) < t1;
+    float xa[NV][8], xb[NV][8];
+#pragma unroll
+    for (int v = 0; v < NV; ++v) {
+      na[v].to_float(xa[v]);
+      nb[v].to_float(xb[v]);
+    }
+    if (t + 2 * K2_WARPS < t1) issue(t + 2 * K2_WARPS);  // next pair in flight while this pair is reduced
     float sa = 0.f, sb = 0.f;
 #pragma unroll
     for (int v = 0; v < NV; ++v)
@@ -146,16 +175,53 @@ __device__ __forceinline__ float block_sum(float v, float* scratch) {
   return s;
 }
 
-// y[o] = W[o,:]·x + bias[o]; warp per output row, coalesced float4-free (stride-32) reads of W.
+// y[o] = W[o,:]·x + bias[o].  A warp owns two output rows per iteration and keeps 8 independent float4 loads in
+// flight (the layers are tiny; latency, not bandwidth, is what matters).  x lives in shared memory.
 __device__ __forceinline__ void dense_rows(const float* __restrict__ W, const float* __restrict__ bias,
                                            const float* x, float* y, int n_out, int n_in) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int o = warp; o < n_out; o += K2_WARPS) {
-    const float* w = W + static_cast<size_t>(o) * n_in;
-    float s = 0.f;
-    for (int j = lane; j < n_in; j += 32) s += __ldg(w + j) * x[j];
-    s = warp_sum(s);
-    if (lane == 0) y[o] = s + __ldg(bias + o);
+  if ((n_in & 3) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0) {
+    const int n4 = n_in >> 2;
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    for (int o = 2 * warp; o < n_out; o += 2 * K2_WARPS) {
+      const bool two = (o + 1) < n_out;
+      const float4* w0 = reinterpret_cast<const float4*>(W + static_cast<size_t>(o) * n_in);
+      const float4* w1 = reinterpret_cast<const float4*>(W + static_cast<size_t>(two ? o + 1 : o) * n_in);
+      float s0 = 0.f, s1 = 0.f;
+      for (int j0 = 0; j0 < n4; j0 += 128) {
+        float4 a[4], c[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = j0 + u * 32 + lane;
+          const bool in = j < n4;
+          a[u] = in ? __ldg(w0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          c[u] = in ? __ldg(w1 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int j = j0 + u * 32 + lane;
+          if (j < n4) {
+            const float4 xv = x4[j];
+            s0 += a[u].x * xv.x + a[u].y * xv.y + a[u].z * xv.z + a[u].w * xv.w;
+            s1 += c[u].x * xv.x + c[u].y * xv.y + c[u].z * xv.z + c[u].w * xv.w;
+          }
+        }
+      }
+      s0 = warp_sum(s0);
+      s1 = warp_sum(s1);
+      if (lane == 0) {
+        y[o] = s0 + __ldg(bias + o);
+        if (two) y[o + 1] = s1 + __ldg(bias + o + 1);
+      }
+    }
+  } else {
+    for (int o = warp; o < n_out; o += K2_WARPS) {
+      const float* w = W + static_cast<size_t>(o) * n_in;
+      float s = 0.f;
+      for (int j = lane; j < n_in; j += 32) s += __ldg(w + j) * x[j];
+      s = warp_sum(s);
+      if (lane == 0) y[o] = s + __ldg(bias + o);
+    }
   }
 }
 
@@ -192,11 +258,11 @@ struct K2HeadParams {
 };
 
 __global__ void __launch_bounds__(K2_THREADS) k2_head_kernel(const K2HeadParams p) {
-  extern __shared__ float sm[];  // pooled[d] | a1[h1] | a2[h2] | lg[C] | scratch[K2_WARPS] | counts (ints)
+  extern __shared__ __align__(16) float sm[];  // pooled[d] | a1[h1] | a2[h2] | lg[64] | scratch[K2_WARPS] | counts
   float* pooled = sm;
-  float* a1 = pooled + p.d;
-  float* a2 = a1 + p.h1;
-  float* lg = a2 + p.h2;
+  float* a1 = pooled + ((p.d + 3) & ~3);
+  float* a2 = a1 + ((p.h1 + 3) & ~3);
+  float* lg = a2 + ((p.h2 + 3) & ~3);
   float* scratch = lg + 64;
   __shared__ int is_last;
   const int b = blockIdx.x;
@@ -219,16 +285,11 @@ __global__ void __launch_bounds__(K2_THREADS) k2_head_kernel(const K2HeadParams 
   __syncthreads();
   if (threadIdx.x == 0) {
     float mx = lg[0];
-    int arg = 0;
-    for (int c = 1; c < p.C; ++c)
-      if (lg[c] > mx) {  // strict > keeps the first maximal index (torch.argmax tie rule)
-        mx = lg[c];
-        arg = c;
-      }
+    for (int c = 1; c < p.C; ++c) mx = fmaxf(mx, lg[c]);
     float den = 0.f;
     for (int c = 0; c < p.C; ++c) den += expf(lg[c] - mx);
-    // argmax is taken over probs in the reference (adapter_router.py:311); softmax is monotone, and ties in
-    // fp32 probs that were not ties in logits are resolved below by re-checking on the computed probs.
+    // argmax is taken over probs like the reference (adapter_router.py:311); strict > keeps the first maximal
+    // index (torch.argmax tie rule).
     float best = -1.f;
     int parg = 0;
     for (int c = 0; c < p.C; ++c) {
@@ -240,7 +301,6 @@ __global__ void __launch_bounds__(K2_THREADS) k2_head_kernel(const K2HeadParams 
         parg = c;
       }
     }
-    (void)arg;
     p.idx[b] = parg;
     __threadfence();
     is_last = (atomicAdd(p.done_counter, 1) == p.B - 1);
@@ -261,18 +321,27 @@ __global__ void __launch_bounds__(K2_THREADS) k2_head_kernel(const K2HeadParams 
 
 int64_t k2_workspace_bytes(int64_t B, int64_t T, int64_t d) {
   if (B <= 0 || T <= 0 || d <= 0) return SAR_EINVAL;
-  const int64_t max_chunks = (T + 7) / 8;  // rows_per_chunk >= 8
+  const int64_t max_chunks = (T + 15) / 16;  // rows_per_chunk >= 16
   return 256 + B * max_chunks * d * 4;
 }
 
 static int k2_rows_per_chunk(int B, int T, int num_sms) {
-  // aim for ~8 CTAs per SM over the whole batch; whole warps-worth of rows, between 8 and 64
-  int64_t target_ctas = static_cast<int64_t>(num_sms) * 8;
-  int64_t rows = (static_cast<int64_t>(B) * T + target_ctas - 1) / target_ctas;
-  rows = (rows + 7) / 8 * 8;
-  if (rows < 8) rows = 8;
-  if (rows > 64) rows = 64;
-  return static_cast<int>(rows);
+  // Rows per CTA: a multiple of 16 (8 warps x 2 frames per iteration) in [16, 128].  Small batches get small chunks
+  // (more CTAs); large batches pick the size whose CTA count wastes the least of the last wave (2 CTAs per SM).
+  const int64_t slots = static_cast<int64_t>(num_sms) * 2;
+  int best = 16;
+  double best_cost = 1e30;
+  for (int rows = 16; rows <= 128; rows += 16) {
+    const int64_t ctas = static_cast<int64_t>(B) * ((T + rows - 1) / rows);
+    const int64_t waves = (ctas + slots - 1) / slots;
+    // time ~ waves * (rows + fixed per-CTA overhead of ~12 rows' worth of latency)
+    const double cost = static_cast<double>(waves) * (rows + 12);
+    if (cost < best_cost - 1e-9) {
+      best_cost = cost;
+      best = rows;
+    }
+  }
+  return best;
 }
 
 template <bool FP32>
@@ -323,7 +392,7 @@ int k2_router_fwd(const K2Args& a, cudaStream_t stream) {
   p.B = a.B; p.T = a.T; p.d = a.d; p.h1 = a.h1; p.h2 = a.h2; p.C = a.C;
   p.logits = a.logits; p.probs = a.probs; p.idx = a.idx; p.perm = a.perm; p.seg_starts = a.seg_starts;
   p.done_counter = counter;
-  const size_t smem = (static_cast<size_t>(a.d) + a.h1 + a.h2 + 64 + K2_WARPS + 80) * sizeof(float);
+  const size_t smem = (static_cast<size_t>(a.d) + a.h1 + a.h2 + 12 + 64 + K2_WARPS + 80) * sizeof(float);
   k2_head_kernel<<<a.B, K2_THREADS, smem, stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail_cuda(e, "k2: head launch");

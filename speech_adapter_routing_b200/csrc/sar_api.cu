@@ -123,6 +123,8 @@ int sar_qv_lora_fwd(const void* x, const void* W, const void* bias, const void* 
   a.B = B; a.T = T; a.d_in = d_in; a.d_out = d_out; a.r = r; a.n_adapters = n_adapters; a.scale = scale;
   a.block_n_override = static_cast<int>((flags >> 8) & 0x3FF);   // debug/tuning: bits [8,18) = BLOCK_N
   a.grid_override = static_cast<int>((flags >> 18) & 0x3FF);     // debug/tuning: bits [18,28) = grid size
+  a.kernel_override = static_cast<int>((flags >> 28) & 0x3);     // debug/tuning: bits [28,30): 1 = single-CTA, 2 = pair
+  a.swap_halves = static_cast<int>((flags >> 1) & 0x1);          // debug: bit 1
   if ((flags & SAR_FLAG_SAVE_U) && !u_out) return fail(SAR_EINVAL, "sar_qv_lora_fwd: SAVE_U without u_out");
   return k1_qv_lora_fwd(a, static_cast<cudaStream_t>(stream));
 }

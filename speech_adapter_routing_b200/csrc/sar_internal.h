@@ -46,8 +46,11 @@ struct K1Args {
   float scale;
   int block_n_override;  // 0 = auto
   int grid_override;     // 0 = auto
+  int kernel_override;   // 0 = auto, 1 = single-CTA kernel, 2 = CTA-pair (cta_group::2) kernel
+  int swap_halves;       // debug switch of the pair kernel's B-operand half assignment
 };
 int k1_qv_lora_fwd(const K1Args& a, cudaStream_t stream);
+int k1v2_qv_lora_fwd(const K1Args& a, int block_n, cudaStream_t stream);
 
 struct K2Args {
   const void* h;

@@ -70,7 +70,8 @@ def pad_rank16(A_stack: torch.Tensor, B_stack: torch.Tensor) -> Tuple[torch.Tens
 def qv_lora_fwd(x: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], A_stack: Optional[torch.Tensor],
                 Bp_stack: Optional[torch.Tensor], utt_adapter: Optional[torch.Tensor], scale: float,
                 save_u: bool = False, block_n: int = 0, grid: int = 0,
-                out: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+                out: Optional[torch.Tensor] = None, kernel: int = 0,
+                swap_halves: bool = False) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
     """K1: y = x·Wᵀ + bias + (scale·x·A_kᵀ)·B_kᵀ with k = utt_adapter[b].  x is [B, T, d_in] bf16."""
     _need_cuda(x, W, bias, A_stack, Bp_stack, utt_adapter)
     if x.dim() != 3:
@@ -91,7 +92,8 @@ def qv_lora_fwd(x: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], 
         utt_adapter = utt_adapter.contiguous()
     y = out if out is not None else torch.empty(B, T, d_out, dtype=torch.bfloat16, device=x.device)
     u = torch.empty(B * T, r, dtype=torch.bfloat16, device=x.device) if (save_u and n_adapters) else None
-    flags = (SAR_FLAG_SAVE_U if u is not None else 0) | ((block_n & 0x3FF) << 8) | ((grid & 0x3FF) << 18)
+    flags = ((SAR_FLAG_SAVE_U if u is not None else 0) | ((block_n & 0x3FF) << 8) | ((grid & 0x3FF) << 18) |
+             ((kernel & 0x3) << 28) | (2 if swap_halves else 0))
     tl = K1_TIMELINE
     if tl is not None:
         ev0 = torch.cuda.Event(enable_timing=True)

@@ -43,7 +43,7 @@ def block_map(diff, tol, rb=32, cb=64):
 
 
 def run_k1_case(name, B, T, d_in, d_out, r, n_adapters, mix="uniform", with_bias=True, base_only_every=0,
-                block_n=0, grid=0, lora=True, seed=1234):
+                block_n=0, grid=0, lora=True, seed=1234, kernel=0, swap=False):
     case = fixtures.make_lora_case(B, T, d_in, d_out, max(r, 8), max(n_adapters, 1), seed=seed, mix=mix,
                                    with_bias=with_bias, base_only_every=base_only_every)
     idx = case.utt_adapter if lora else torch.full((B,), -1, dtype=torch.int32)
@@ -54,7 +54,8 @@ def run_k1_case(name, B, T, d_in, d_out, r, n_adapters, mix="uniform", with_bias
         A = case.A_stack.to(DEV); Bp = ops.pack_lora_b(case.B_stack.to(DEV)); ia = idx.to(DEV)
     else:
         A = Bp = ia = None
-    y, _ = ops.qv_lora_fwd(x, W, bias, A, Bp, ia, case.scaling, block_n=block_n, grid=grid)
+    y, _ = ops.qv_lora_fwd(x, W, bias, A, Bp, ia, case.scaling, block_n=block_n, grid=grid, kernel=kernel,
+                           swap_halves=swap)
     torch.cuda.synchronize()
     mx, rel, diff = err_stats(y, ref)
     ok = rel < 2e-2
@@ -94,6 +95,31 @@ def suite_k1():
     ok &= run_k1_case("lora T=1 decode-shaped", 16, 1, 768, 768, 16, 4)
     ok &= run_k1_case("lora B=64 T=1500", 64, 1500, 768, 768, 16, 4)
     log("[k1] suite", "PASSED" if ok else "FAILED")
+    return ok
+
+
+def suite_k1v2():
+    ok = True
+    K = dict(kernel=2)
+    a = run_k1_case("v2 base 1 unit (swap=0)", 1, 256, 64, 128, 16, 0, lora=False, with_bias=False, **K)
+    b = run_k1_case("v2 base 1 unit (swap=1)", 1, 256, 64, 128, 16, 0, lora=False, with_bias=False, swap=True, **K)
+    log(f"[k1v2] half assignment: swap=0 {'OK' if a else 'FAIL'}, swap=1 {'OK' if b else 'FAIL'}")
+    ok &= a
+    ok &= run_k1_case("v2 base K=768 N=768 bn192", 1, 256, 768, 768, 16, 0, lora=False, **K)
+    ok &= run_k1_case("v2 base bn128", 1, 256, 768, 768, 16, 0, lora=False, block_n=128, **K)
+    ok &= run_k1_case("v2 base tail T=300", 1, 300, 768, 768, 16, 0, lora=False, **K)
+    ok &= run_k1_case("v2 base T=1500 B=2", 2, 1500, 768, 768, 16, 0, lora=False, **K)
+    ok &= run_k1_case("v2 lora r16 1 unit", 1, 256, 768, 768, 16, 1, mix="single", **K)
+    ok &= run_k1_case("v2 lora r16 4 adapters", 8, 300, 768, 768, 16, 4, **K)
+    ok &= run_k1_case("v2 lora mid-unit ranges (5 pairs)", 3, 256, 768, 768, 16, 4, grid=10, **K)
+    ok &= run_k1_case("v2 lora 1 pair serial", 4, 260, 768, 768, 16, 4, grid=2, **K)
+    ok &= run_k1_case("v2 lora r32 1024 bn128", 6, 200, 1024, 1024, 32, 4, **K)
+    ok &= run_k1_case("v2 lora r64 1280 bn128", 9, 130, 1280, 1280, 64, 8, **K)
+    ok &= run_k1_case("v2 lora r48", 3, 130, 768, 768, 48, 2, **K)
+    ok &= run_k1_case("v2 lora + base-only utts", 8, 200, 768, 768, 16, 4, base_only_every=3, **K)
+    ok &= run_k1_case("v2 lora T=100 (half pair empty)", 5, 100, 768, 768, 16, 4, **K)
+    ok &= run_k1_case("v2 lora B=64 T=1500", 64, 1500, 768, 768, 16, 4, **K)
+    log("[k1v2] suite", "PASSED" if ok else "FAILED")
     return ok
 
 
@@ -195,21 +221,22 @@ def suite_perf():
         ia = torch.randint(0, n, (B,), generator=g).to(torch.int32).to(DEV)
         flops = 2.0 * B * T * d * d + 2.0 * B * T * r * 2 * d
         for bn in ([128, 192] if d % 192 == 0 else [128]):
+          for kern in (1, 2):
             it = [0]
 
             def f():
                 i = it[0] % nbuf
                 it[0] += 1
-                ops.qv_lora_fwd(xs[i], W, bias, A, Bp, ia, 2.0, block_n=bn, out=ys[i])
+                ops.qv_lora_fwd(xs[i], W, bias, A, Bp, ia, 2.0, block_n=bn, out=ys[i], kernel=kern)
             ms = timeit(f)
-            log(f"[perf] k1 lora  d={d} r={r} bn={bn}: {ms*1e3:.1f} us  {flops/ms/1e9:.1f} TFLOP/s")
+            log(f"[perf] k1v{kern} lora  d={d} r={r} bn={bn}: {ms*1e3:.1f} us  {flops/ms/1e9:.1f} TFLOP/s")
 
             def fb():
                 i = it[0] % nbuf
                 it[0] += 1
-                ops.qv_lora_fwd(xs[i], W, bias, None, None, None, 2.0, block_n=bn, out=ys[i])
+                ops.qv_lora_fwd(xs[i], W, bias, None, None, None, 2.0, block_n=bn, out=ys[i], kernel=kern)
             ms = timeit(fb)
-            log(f"[perf] k1 base  d={d} bn={bn}: {ms*1e3:.1f} us  {2.0*B*T*d*d/ms/1e9:.1f} TFLOP/s")
+            log(f"[perf] k1v{kern} base  d={d} bn={bn}: {ms*1e3:.1f} us  {2.0*B*T*d*d/ms/1e9:.1f} TFLOP/s")
 
         def fc():
             i = it[0] % nbuf
