@@ -89,6 +89,68 @@ int sar_qv_lora_fwd(const void* x, const void* W, const void* bias, const void* 
                     uint32_t flags, void* stream);
 
 /*
+ * Fused attention-projection stage: up to three projections of the SAME input in one launch,
+ * with the routed low-rank term on any of them, the query scale folded into the epilogue and, optionally, the
+ * [B,T,d] -> [B,h,T,64] head-major transpose done by the TMA store / load instead of separate copy kernels.
+ *   seg s:  y_s = ( x·W_sᵀ + bias_s + (scale·x·A_{set,k}ᵀ)·B_{set,k}ᵀ ) * seg_scale[s],  set = seg_set[s] (-1: no LoRA)
+ * Replaces, for one WhisperAttention.forward call ($HF/models/whisper/modeling_whisper.py:310-336): q_proj (LoRA) and
+ * `* self.scaling` (:310), k_proj (:331), v_proj (LoRA, :332) and the three `.transpose(1, 2).contiguous()` copies
+ * (:311-312, :333-334); with x_head_major = 1 and n_seg = 1 it is out_proj reading SDPA's output in place (:352-353).
+ *
+ *   x         bf16 [B, T, d_in]  or, if x_head_major, [B, d_in/64, T, 64]
+ *   W_cat     bf16 [n_seg*d_out, d_in]   weights of the segments concatenated along the output dimension
+ *   bias_cat  bf16 [n_seg*d_out] or NULL (k_proj has no bias: pass zeros in its slice)
+ *   A_cat     bf16 [n_sets*n_adapters, r, d_in];  Bp_cat bf16 [n_sets*n_adapters, d_out, SAR_RPAD]
+ *   y         n_seg output pointers, each bf16 [B, T, d_out] or, if y_head_major, [B, d_out/64, T, 64]
+ * Constraints: head dim 64 for the head-major modes; d_out % 128 == 0; r in {16,32,48,64}; n_sets <= 2; n_seg <= 3.
+ */
+int sar_attn_proj_fwd(const void* x, int x_head_major, const void* W_cat, const void* bias_cat, const void* A_cat,
+                      const void* Bp_cat, const int32_t* utt_adapter, void* const* y, const int32_t* seg_set,
+                      const float* seg_scale, int n_seg, int n_sets, int y_head_major, int B, int T, int d_in,
+                      int d_out, int r, int n_adapters, float scale, uint32_t flags, void* stream);
+
+/* epilogue activations of sar_linear_fwd */
+#define SAR_ACT_NONE 0
+#define SAR_ACT_GELU 1 /* erf-form GELU, HF ACT2FN["gelu"] */
+
+/*
+ * Self-attention q‖v pair: one x, two LoRA'd projections, two row-major outputs.
+ *   y_q = x·W_qᵀ + b_q + (scale·x·A_{q,k}ᵀ)·B_{q,k}ᵀ ;  y_v likewise.  Thin wrapper over sar_attn_proj_fwd
+ *   (n_seg = 2, n_sets = 2); W_cat = [W_q; W_v], A_cat = [A_q stack; A_v stack], Bp_cat likewise.
+ * Replaces the q_proj + v_proj calls of one WhisperAttention.forward ($HF/modeling_whisper.py:310, :332).
+ */
+int sar_qv_lora_fwd_pair(const void* x, const void* W_cat, const void* bias_cat, const void* A_cat,
+                         const void* Bp_cat, const int32_t* utt_adapter, void* y_q, void* y_v, int B,
+                         int T, int d_in, int d_out, int r, int n_adapters, float scale, uint32_t flags,
+                         void* stream);
+
+/*
+ * Plain dense layer of the Whisper block on the same tcgen05 pair kernel, with the neighbouring elementwise ops
+ * folded into the epilogue:
+ *   y = act(x·Wᵀ + bias) + residual
+ * Replaces, per layer, out_proj + `residual + h` ($HF/modeling_whisper.py:352-353 + :399 / :481 / :495), fc1 + GELU
+ * (:403 / :500) and fc2 + `residual + h` (:405-407 / :502-504), including the `.transpose(1,2).contiguous()` of
+ * SDPA's output when x_head_major = 1.
+ *   x        bf16 [B, T, d_in]  or, if x_head_major, [B, d_in/64, T, 64]
+ *   W        bf16 [d_out, d_in];  bias bf16 [d_out] or NULL
+ *   residual bf16 [B, T, d_out] or NULL (may alias y)
+ *   y        bf16 [B, T, d_out]
+ * Constraints: d_in % 64 == 0, d_out % 128 == 0, pointers 16-byte aligned.
+ */
+int sar_linear_fwd(const void* x, int x_head_major, const void* W, const void* bias, const void* residual,
+                   void* y, int B, int T, int d_in, int d_out, int act, uint32_t flags, void* stream);
+
+/*
+ * LayerNorm over the last dimension, fp32 statistics, bf16 in / out (HBM-bound: one read + one write of x):
+ *   y[m,:] = (x[m,:] - mean) * rsqrt(var + eps) * gamma + beta
+ * Replaces nn.LayerNorm at self_attn_layer_norm / encoder_attn_layer_norm / final_layer_norm / layer_norm
+ * ($HF/modeling_whisper.py:391, :401, :470, :486, :498, :643, :797).
+ *   x, y bf16 [M, d];  gamma, beta bf16 [d].  Constraints: d % 8 == 0, d <= 2048.
+ */
+int sar_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, int64_t M, int d, float eps,
+                      void* stream);
+
+/*
  * Row-indexed variant for decode steps (T = 1 per utterance, rows of different adapters share a tile):
  *   y[m,:] = x[m,:]·Wᵀ + bias + scale·(x[m,:]·A_kᵀ)·B_kᵀ, k = row_adapter[m].
  * Replaces the per-sample adapter.generate loop of src/models/adapter_router.py:744-750 for the

@@ -19,6 +19,7 @@ SAR_OK, SAR_EINVAL, SAR_EARCH, SAR_ECUDA, SAR_EWORKSPACE = 0, -1, -2, -3, -4
 SAR_FLAG_SAVE_U = 1
 SAR_OP_QV_LORA_FWD, SAR_OP_ROUTER_FWD, SAR_OP_QV_LORA_BWD, SAR_OP_QV_LORA_FWD_ROWS = 0, 1, 2, 3
 SAR_RPAD = 64
+SAR_ACT_NONE, SAR_ACT_GELU = 0, 1
 
 # name -> (restype, argtypes); mirrors include/sar.h one to one
 _SIGNATURES = {
@@ -27,6 +28,10 @@ _SIGNATURES = {
     "sar_device_ok": (c_int, []),
     "sar_workspace_bytes": (c_int64, [c_int, c_int64, c_int64, c_int64, c_int64, c_int64]),
     "sar_qv_lora_fwd": (c_int, [c_void_p] * 5 + [c_void_p, c_void_p, c_void_p] + [c_int] * 6 + [c_float, c_uint32, c_void_p]),
+    "sar_attn_proj_fwd": (c_int, [c_void_p, c_int] + [c_void_p] * 8 + [c_int] * 9 + [c_float, c_uint32, c_void_p]),
+    "sar_qv_lora_fwd_pair": (c_int, [c_void_p] * 8 + [c_int] * 6 + [c_float, c_uint32, c_void_p]),
+    "sar_linear_fwd": (c_int, [c_void_p, c_int] + [c_void_p] * 4 + [c_int] * 5 + [c_uint32, c_void_p]),
+    "sar_layernorm_fwd": (c_int, [c_void_p] * 4 + [c_int64, c_int, c_float, c_void_p]),
     "sar_qv_lora_fwd_rows": (c_int, [c_void_p] * 5 + [c_void_p, c_void_p] + [c_int] * 5 + [c_float, c_void_p, c_void_p]),
     "sar_router_fwd": (c_int, [c_void_p, c_int] + [c_void_p] * 12 + [c_int] * 6 + [c_void_p] * 5 + [c_void_p, c_void_p]),
     "sar_qv_lora_bwd": (c_int, [c_void_p] * 7 + [c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 6 + [c_float, c_void_p, c_void_p]),

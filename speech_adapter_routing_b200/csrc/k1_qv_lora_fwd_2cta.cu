@@ -28,15 +28,28 @@ constexpr int V2_MAX_STAGES = 8;
 struct K1V2Params {
   int B, T, d_in, d_out, r;
   int tiles_per_utt;   // 256-row tiles per utterance
-  int n_tiles, k_blocks, num_stages, n_adapters;
+  int n_tiles;         // N tiles over ALL segments (n_seg * nt_per_seg)
+  int nt_per_seg;      // N tiles per output segment (d_out / BLOCK_N)
+  int n_seg;           // output segments sharing x: 1 (q or v), 2 (k|v), 3 (q|k|v)
+  int n_sets;          // LoRA sets (A/B stacks) in use: 1 or 2
+  int seg_set[3];      // LoRA set of each segment, -1 = none (k_proj)
+  float seg_scale[3];  // epilogue scale of each segment (head_dim^-0.5 for q)
+  int x_head_major;    // x is [B, h, T, 64] (SDPA output): K block kb <-> head kb
+  int y_head_major;    // y is [B, h, T, 64] (SDPA input layout)
+  int k_blocks, num_stages, n_adapters;
   long long total_steps;  // num_units * n_tiles
   int num_pairs;
   int swap_halves;     // debug: which CTA of the pair supplies the upper half of every B operand
   float scale;
   const int32_t* utt_adapter;
   const __nv_bfloat16* bias;
+  const __nv_bfloat16* residual;   // [B, T, d_out] added in the epilogue (n_seg == 1, row-major y), or null
+  int act;                         // SAR_ACT_*: 0 none, 1 erf-GELU applied to (acc + bias) before the residual
   __nv_bfloat16* u_out;
 };
+
+// erf-form GELU (HF ACT2FN["gelu"], what Whisper's fc1 uses): 0.5 v (1 + erf(v / sqrt 2))
+__device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
 
 template <int BLOCK_N>
 struct V2Smem {
@@ -44,28 +57,32 @@ struct V2Smem {
   static constexpr int BPH_BYTES = (BLOCK_N / 2) * 128;
   static __host__ __device__ int ah_bytes(int r) { return (r / 2) * 128; }                      // bytes TMA writes
   static __host__ __device__ int ah_slot(int r) { return ((r / 2) * 128 + 1023) & ~1023; }      // 1 KB-aligned slot
-  static __host__ __device__ int stage_bytes(int r) { return V2_X_BYTES + WH_BYTES + ah_slot(r); }
-  static __host__ __device__ int fixed_bytes() { return V2_U_BYTES + BPH_BYTES + 4 * 2 * V2_STG_BYTES + 512; }
+  static __host__ __device__ int stage_bytes(int r, int n_sets) { return V2_X_BYTES + WH_BYTES + n_sets * ah_slot(r); }
+  static __host__ __device__ int fixed_bytes(int n_sets) {
+    return n_sets * V2_U_BYTES + BPH_BYTES + 4 * 2 * V2_STG_BYTES + 512;
+  }
 };
 
 template <int BLOCK_N>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V2_THREADS, 1)
 k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
             const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-            const __grid_constant__ CUtensorMap tm_y, const K1V2Params p) {
+            const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUtensorMap tm_y1,
+            const __grid_constant__ CUtensorMap tm_y2, const K1V2Params p) {
   using L = V2Smem<BLOCK_N>;
   constexpr int TMEM_COLS = 512;
-  constexpr int U_COL = 2 * BLOCK_N;
-  static_assert(2 * BLOCK_N + 64 <= TMEM_COLS, "TMEM budget");
+  constexpr int U_COL = 2 * BLOCK_N;   // U accumulators: set s at columns [U_COL + 64 s, U_COL + 64 s + r)
+  static_assert(2 * BLOCK_N + 2 * 64 <= TMEM_COLS, "TMEM budget");
   static_assert(BLOCK_N % 64 == 0 && BLOCK_N <= 256, "BLOCK_N");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int S = p.num_stages;
-  const int stage_bytes = L::stage_bytes(p.r);
+  const int stage_bytes = L::stage_bytes(p.r, p.n_sets);
+  const int ah_slot = L::ah_slot(p.r);
   uint8_t* stages = smem;
-  uint8_t* u_tile = stages + S * stage_bytes;
-  uint8_t* bp_tile = u_tile + V2_U_BYTES;
+  uint8_t* u_tile = stages + S * stage_bytes;          // [n_sets][16 KB]
+  uint8_t* bp_tile = u_tile + p.n_sets * V2_U_BYTES;
   uint8_t* stg = bp_tile + L::BPH_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(stg + 4 * 2 * V2_STG_BYTES);
   uint64_t* full = bars;                          // [S]  leader only (count 1 + tx of BOTH CTAs)
@@ -89,7 +106,9 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm_x);
     tma_prefetch_desc(&tm_w);
-    tma_prefetch_desc(&tm_y);
+    tma_prefetch_desc(&tm_y0);
+    if (p.n_seg > 1) tma_prefetch_desc(&tm_y1);
+    if (p.n_seg > 2) tma_prefetch_desc(&tm_y2);
     if (has_lora) {
       tma_prefetch_desc(&tm_a);
       tma_prefetch_desc(&tm_b);
@@ -119,6 +138,7 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
 
   const int KB = p.k_blocks;
   const int NT = p.n_tiles;
+  const int NTS = p.nt_per_seg;
   const int bp_issue_kb = KB > 2 ? KB / 2 : 0;
   const long long g0 = p.total_steps * pair / p.num_pairs;
   const long long g1 = p.total_steps * (pair + 1) / p.num_pairs;
@@ -133,24 +153,33 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
       uint32_t phase = 0;
       uint32_t b_uses = 0;
       const uint32_t b_full_leader = leader_addr(b_full);
-      auto k_loop = [&](int b, int m0, int k, int n0, bool main, bool with_a, bool with_bp) {
-        const uint32_t tx_cta = V2_X_BYTES + (main ? L::WH_BYTES : 0) + (with_a ? L::ah_bytes(p.r) : 0);
+      // nt = N tile over all segments (-1 = U-only pass); bp_set = LoRA set whose B_k tile this N tile needs (-1 none)
+      auto k_loop = [&](int b, int m0, int k, int nt, bool with_a, int bp_set) {
+        const bool main = nt >= 0;
+        const uint32_t tx_cta =
+            V2_X_BYTES + (main ? L::WH_BYTES : 0) + (with_a ? p.n_sets * L::ah_bytes(p.r) : 0);
         for (int kb = 0; kb < KB; ++kb) {
-          if (with_bp && kb == bp_issue_kb) {
+          if (bp_set >= 0 && kb == bp_issue_kb) {
             mbar_wait(b_empty, (b_uses & 1) ^ 1);
             if (leader) mbar_arrive_expect_tx(b_full, 2 * L::BPH_BYTES);
-            tma_load_2d_2sm(bp_tile, &tm_b, b_full_leader, 0, k * p.d_out + n0 + half * (BLOCK_N / 2));
+            tma_load_2d_2sm(bp_tile, &tm_b, b_full_leader, 0,
+                            (bp_set * p.n_adapters + k) * p.d_out + (nt % NTS) * BLOCK_N + half * (BLOCK_N / 2));
             ++b_uses;
           }
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* st = stages + stage * stage_bytes;
           const uint32_t full_leader = leader_addr(&full[stage]);
           if (leader) mbar_arrive_expect_tx(&full[stage], 2 * tx_cta);
-          tma_load_3d_2sm(st, &tm_x, full_leader, kb * V2_BLOCK_K, m0, b);
-          if (main) tma_load_2d_2sm(st + V2_X_BYTES, &tm_w, full_leader, kb * V2_BLOCK_K, n0 + half * (BLOCK_N / 2));
+          if (p.x_head_major)
+            tma_load_4d_2sm(st, &tm_x, full_leader, 0, m0, kb, b);
+          else
+            tma_load_3d_2sm(st, &tm_x, full_leader, kb * V2_BLOCK_K, m0, b);
+          if (main)
+            tma_load_2d_2sm(st + V2_X_BYTES, &tm_w, full_leader, kb * V2_BLOCK_K, nt * BLOCK_N + half * (BLOCK_N / 2));
           if (with_a)
-            tma_load_2d_2sm(st + V2_X_BYTES + L::WH_BYTES, &tm_a, full_leader, kb * V2_BLOCK_K,
-                            k * p.r + half * (p.r / 2));
+            for (int s = 0; s < p.n_sets; ++s)
+              tma_load_2d_2sm(st + V2_X_BYTES + L::WH_BYTES + s * ah_slot, &tm_a, full_leader, kb * V2_BLOCK_K,
+                              (s * p.n_adapters + k) * p.r + half * (p.r / 2));
           if (++stage == S) {
             stage = 0;
             phase ^= 1;
@@ -166,8 +195,9 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
         const int m0 = (unit - b * p.tiles_per_utt) * 256 + rank * V2_ROWS_PER_CTA;
         int k = has_lora ? p.utt_adapter[b] : -1;
         if (k < 0 || k >= p.n_adapters) k = -1;
-        if (k >= 0 && nt_first > 0) k_loop(b, m0, k, 0, false, true, false);   // U-only pass
-        for (int nt = nt_first; nt < nt_last; ++nt) k_loop(b, m0, k, nt * BLOCK_N, true, k >= 0 && nt == 0, k >= 0);
+        if (k >= 0 && nt_first > 0) k_loop(b, m0, k, -1, true, -1);   // U-only pass
+        for (int nt = nt_first; nt < nt_last; ++nt)
+          k_loop(b, m0, k, nt, k >= 0 && nt == 0, k >= 0 ? p.seg_set[nt / NTS] : -1);
         g += nt_last - nt_first;
       }
     }
@@ -195,10 +225,12 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
               umma_bf16_2sm(acc, xd + 2 * kk, wd + 2 * kk, idesc_main, (kb | kk) != 0);
           }
           if (with_a) {
-            const uint64_t ad = umma_desc_sw128(st + V2_X_BYTES + L::WH_BYTES);
+            for (int s = 0; s < p.n_sets; ++s) {
+              const uint64_t ad = umma_desc_sw128(st + V2_X_BYTES + L::WH_BYTES + s * ah_slot);
 #pragma unroll
-            for (int kk = 0; kk < V2_BLOCK_K / 16; ++kk)
-              umma_bf16_2sm(tmem_base + U_COL, xd + 2 * kk, ad + 2 * kk, idesc_u, (kb | kk) != 0);
+              for (int kk = 0; kk < V2_BLOCK_K / 16; ++kk)
+                umma_bf16_2sm(tmem_base + U_COL + 64 * s, xd + 2 * kk, ad + 2 * kk, idesc_u, (kb | kk) != 0);
+            }
           }
           umma_commit_2sm(&empty[stage], 0b11);
           if (++stage == S) {
@@ -231,11 +263,12 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
           mbar_wait(&tmem_empty[buf], ((tile_iter >> 1) & 1) ^ 1);
           tc_fence_after();
           k_loop(acc, true, k >= 0 && nt == 0);
-          if (k >= 0) {
-            if (nt == 0) publish_u();
+          if (k >= 0 && nt == 0) publish_u();
+          const int set = k >= 0 ? p.seg_set[nt / NTS] : -1;
+          if (set >= 0) {
             mbar_wait(b_full, b_uses & 1);
             tc_fence_after();
-            const uint64_t ud = umma_desc_sw128(u_desc_base);
+            const uint64_t ud = umma_desc_sw128(u_desc_base + set * V2_U_BYTES);
             const uint64_t bd = umma_desc_sw128(bp_desc_base);
             const int ksteps = p.r >> 4;
             for (int kk = 0; kk < ksteps; ++kk) umma_bf16_2sm(acc, ud + 2 * kk, bd + 2 * kk, idesc_main, 1u);
@@ -271,24 +304,26 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
         // ---- U: TMEM fp32 -> scale -> bf16 -> swizzled smem A-operand tile of THIS CTA (+ optional global save)
         mbar_wait(u_full, lora_units & 1);
         tc_fence_after();
-        const uint32_t u_row = smem_u32(u_tile) + row * 128;
-        // the unit's rows are saved exactly once: by the range that owns its N-tile 0
+        // the unit's rows are saved exactly once: by the range that owns its N-tile 0 (single-set calls only)
         const bool save = (p.u_out != nullptr) && (nt_first == 0) && (m0 + row < p.T);
         uint4* u_dst = save ? reinterpret_cast<uint4*>(p.u_out + (static_cast<size_t>(b) * p.T + m0 + row) * p.r)
                             : nullptr;
-        for (int j = 0; j < (p.r >> 4); ++j) {
-          uint32_t v[16];
-          tmem_ld_32x16(tmem_base + lane_addr + U_COL + j * 16, v);
-          tmem_ld_wait();
-          uint32_t pk[8];
+        for (int s = 0; s < p.n_sets; ++s) {
+          const uint32_t u_row = smem_u32(u_tile) + s * V2_U_BYTES + row * 128;
+          for (int j = 0; j < (p.r >> 4); ++j) {
+            uint32_t v[16];
+            tmem_ld_32x16(tmem_base + lane_addr + U_COL + 64 * s + j * 16, v);
+            tmem_ld_wait();
+            uint32_t pk[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            pk[i] = pack_bf16x2(__uint_as_float(v[2 * i]) * p.scale, __uint_as_float(v[2 * i + 1]) * p.scale);
-          st_shared_v4(u_row + (((2 * j) ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
-          st_shared_v4(u_row + (((2 * j + 1) ^ sw) << 4), pk[4], pk[5], pk[6], pk[7]);
-          if (save) {
-            u_dst[2 * j] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-            u_dst[2 * j + 1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            for (int i = 0; i < 8; ++i)
+              pk[i] = pack_bf16x2(__uint_as_float(v[2 * i]) * p.scale, __uint_as_float(v[2 * i + 1]) * p.scale);
+            st_shared_v4(u_row + (((2 * j) ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
+            st_shared_v4(u_row + (((2 * j + 1) ^ sw) << 4), pk[4], pk[5], pk[6], pk[7]);
+            if (save && s == 0) {
+              u_dst[2 * j] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              u_dst[2 * j + 1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            }
           }
         }
         tc_fence_before();
@@ -299,7 +334,11 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
       }
       for (int nt = nt_first; nt < nt_last; ++nt, ++tile_iter) {
         const uint32_t buf = tile_iter & 1;
-        const int n0 = nt * BLOCK_N;
+        const int n0 = nt * BLOCK_N;                 // column in the concatenated N space (W_cat / bias_cat rows)
+        const int seg = nt / NTS;
+        const int n0_seg = (nt - seg * NTS) * BLOCK_N;   // column inside this segment's output tensor
+        const float oscale = p.seg_scale[seg];
+        const CUtensorMap* ty = seg == 0 ? &tm_y0 : (seg == 1 ? &tm_y1 : &tm_y2);
         mbar_wait(&tmem_full[buf], (tile_iter >> 1) & 1);
         tc_fence_after();
         const bool rows_live = (m0 + q * 32) < p.T;
@@ -309,6 +348,18 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
           const uint32_t taddr = tmem_base + lane_addr + buf * BLOCK_N + c * 64;
           tmem_ld_32x32(taddr, v0);
           tmem_ld_32x32(taddr + 32, v1);
+          uint4 rs[8];
+          if (p.residual != nullptr) {   // this thread's 64 residual columns (one 128-byte line), in flight under the TMEM load
+            if (m0 + row < p.T) {
+              const uint4* rp = reinterpret_cast<const uint4*>(
+                  p.residual + (static_cast<size_t>(b) * p.T + m0 + row) * p.d_out + n0_seg + c * 64);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) rs[j] = __ldg(rp + j);
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) rs[j] = make_uint4(0u, 0u, 0u, 0u);
+            }
+          }
           if (lane == 0) tma_store_wait_read<1>();
           __syncwarp();
           tmem_ld_wait();
@@ -334,16 +385,30 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int e = 8 * j + 2 * i;
-              const float a0 = __uint_as_float(e < 32 ? v0[e & 31] : v1[e & 31]);
-              const float a1 = __uint_as_float(e < 32 ? v0[(e + 1) & 31] : v1[(e + 1) & 31]);
-              pk[i] = pack_bf16x2(a0 + bf[2 * i], a1 + bf[2 * i + 1]);
+              float a0 = __uint_as_float(e < 32 ? v0[e & 31] : v1[e & 31]) + bf[2 * i];
+              float a1 = __uint_as_float(e < 32 ? v0[(e + 1) & 31] : v1[(e + 1) & 31]) + bf[2 * i + 1];
+              if (p.act == SAR_ACT_GELU) {
+                a0 = gelu_erf(a0);
+                a1 = gelu_erf(a1);
+              }
+              a0 *= oscale;
+              a1 *= oscale;
+              if (p.residual != nullptr) {
+                const uint32_t rw = i == 0 ? rs[j].x : (i == 1 ? rs[j].y : (i == 2 ? rs[j].z : rs[j].w));
+                a0 += __uint_as_float(rw << 16);
+                a1 += __uint_as_float(rw & 0xFFFF0000u);
+              }
+              pk[i] = pack_bf16x2(a0, a1);
             }
             st_shared_v4(srow + ((static_cast<uint32_t>(j) ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
           }
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0 && rows_live) {
-            tma_store_3d(&tm_y, sbuf, n0 + c * 64, m0 + q * 32, b);
+            if (p.y_head_major)
+              tma_store_4d(ty, sbuf, 0, m0 + q * 32, (n0_seg >> 6) + c, b);
+            else
+              tma_store_3d(ty, sbuf, n0_seg + c * 64, m0 + q * 32, b);
             tma_store_commit();
           }
           ++stg_idx;
@@ -372,11 +437,23 @@ static int k1v2_launch(const K1Args& a, cudaStream_t stream) {
   using L = V2Smem<BLOCK_N>;
   const DeviceInfo& dev = device_info();
   const bool has_lora = a.n_adapters > 0 && a.utt_adapter != nullptr && a.A_stack != nullptr && a.Bp_stack != nullptr;
+  const int n_seg = a.n_seg > 0 ? a.n_seg : 1;
+  const int n_sets = (has_lora && a.n_sets > 0) ? a.n_sets : 1;
 
   K1V2Params p{};
   p.B = a.B; p.T = a.T; p.d_in = a.d_in; p.d_out = a.d_out; p.r = has_lora ? a.r : 16;
   p.tiles_per_utt = (a.T + 255) / 256;
-  p.n_tiles = a.d_out / BLOCK_N;
+  p.nt_per_seg = a.d_out / BLOCK_N;
+  p.n_seg = n_seg;
+  p.n_tiles = n_seg * p.nt_per_seg;
+  p.n_sets = n_sets;
+  for (int s = 0; s < 3; ++s) {
+    p.seg_set[s] = a.n_seg > 0 ? a.seg_set[s] : 0;
+    p.seg_scale[s] = a.n_seg > 0 ? a.seg_scale[s] : 1.0f;
+    if (p.seg_set[s] >= n_sets) return fail(SAR_EINVAL, "k1v2: segment refers to a LoRA set that does not exist");
+  }
+  p.x_head_major = a.x_head_major;
+  p.y_head_major = a.y_head_major;
   p.k_blocks = a.d_in / V2_BLOCK_K;
   p.n_adapters = has_lora ? a.n_adapters : 0;
   p.total_steps = static_cast<long long>(a.B) * p.tiles_per_utt * p.n_tiles;
@@ -384,52 +461,73 @@ static int k1v2_launch(const K1Args& a, cudaStream_t stream) {
   p.swap_halves = a.swap_halves;
   p.utt_adapter = has_lora ? a.utt_adapter : nullptr;
   p.bias = reinterpret_cast<const __nv_bfloat16*>(a.bias);
-  p.u_out = has_lora ? reinterpret_cast<__nv_bfloat16*>(a.u_out) : nullptr;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(a.residual);
+  p.act = a.act;
+  if (p.residual && (n_seg != 1 || a.y_head_major))
+    return fail(SAR_EINVAL, "k1v2: residual needs one row-major output segment");
+  p.u_out = (has_lora && n_sets == 1) ? reinterpret_cast<__nv_bfloat16*>(a.u_out) : nullptr;
 
-  const int stage_bytes = L::stage_bytes(p.r);
-  const int budget = dev.max_smem_optin - 1024 - L::fixed_bytes();
+  const int stage_bytes = L::stage_bytes(p.r, n_sets);
+  const int budget = dev.max_smem_optin - 1024 - L::fixed_bytes(n_sets);
   int S = budget / stage_bytes;
   if (S > V2_MAX_STAGES) S = V2_MAX_STAGES;
   if (S < 2) return fail(SAR_EINVAL, "k1v2: shared memory budget too small for this shape");
   p.num_stages = S;
-  const int smem_bytes = 1024 + S * stage_bytes + L::fixed_bytes();
+  const int smem_bytes = 1024 + S * stage_bytes + L::fixed_bytes(n_sets);
 
   int pairs = dev.num_sms / 2;
   if (p.total_steps < pairs) pairs = static_cast<int>(p.total_steps);
   if (a.grid_override > 0 && a.grid_override / 2 >= 1 && a.grid_override / 2 < pairs) pairs = a.grid_override / 2;
   p.num_pairs = pairs;
 
-  CUtensorMap tm_x, tm_w, tm_a, tm_b, tm_y;
+  CUtensorMap tm_x, tm_w, tm_a, tm_b, tm_y[3];
   memset(&tm_a, 0, sizeof(tm_a));
   memset(&tm_b, 0, sizeof(tm_b));
+  memset(tm_y, 0, sizeof(tm_y));
   int rc;
-  {
+  if (a.x_head_major) {
+    const uint64_t h = a.d_in / 64;
+    const uint64_t dims[4] = {64, (uint64_t)a.T, h, (uint64_t)a.B};
+    const uint64_t strides[3] = {128, (uint64_t)a.T * 128, h * a.T * 128};
+    const uint32_t box[4] = {64, V2_ROWS_PER_CTA, 1, 1};
+    if ((rc = make_tmap_bf16(&tm_x, a.x, 4, dims, strides, box))) return rc;
+  } else {
     const uint64_t dims[3] = {(uint64_t)a.d_in, (uint64_t)a.T, (uint64_t)a.B};
     const uint64_t strides[2] = {(uint64_t)a.d_in * 2, (uint64_t)a.T * a.d_in * 2};
     const uint32_t box[3] = {V2_BLOCK_K, V2_ROWS_PER_CTA, 1};
     if ((rc = make_tmap_bf16(&tm_x, a.x, 3, dims, strides, box))) return rc;
   }
-  {
-    const uint64_t dims[3] = {(uint64_t)a.d_out, (uint64_t)a.T, (uint64_t)a.B};
-    const uint64_t strides[2] = {(uint64_t)a.d_out * 2, (uint64_t)a.T * a.d_out * 2};
-    const uint32_t box[3] = {64, 32, 1};
-    if ((rc = make_tmap_bf16(&tm_y, a.y, 3, dims, strides, box))) return rc;
+  for (int s = 0; s < n_seg; ++s) {
+    void* yp = a.n_seg > 0 ? a.y_seg[s] : a.y;
+    if (!yp) return fail(SAR_EINVAL, "k1v2: null output segment");
+    if (a.y_head_major) {
+      const uint64_t h = a.d_out / 64;
+      const uint64_t dims[4] = {64, (uint64_t)a.T, h, (uint64_t)a.B};
+      const uint64_t strides[3] = {128, (uint64_t)a.T * 128, h * a.T * 128};
+      const uint32_t box[4] = {64, 32, 1, 1};
+      if ((rc = make_tmap_bf16(&tm_y[s], yp, 4, dims, strides, box))) return rc;
+    } else {
+      const uint64_t dims[3] = {(uint64_t)a.d_out, (uint64_t)a.T, (uint64_t)a.B};
+      const uint64_t strides[2] = {(uint64_t)a.d_out * 2, (uint64_t)a.T * a.d_out * 2};
+      const uint32_t box[3] = {64, 32, 1};
+      if ((rc = make_tmap_bf16(&tm_y[s], yp, 3, dims, strides, box))) return rc;
+    }
   }
   {
-    const uint64_t dims[2] = {(uint64_t)a.d_in, (uint64_t)a.d_out};
+    const uint64_t dims[2] = {(uint64_t)a.d_in, (uint64_t)n_seg * a.d_out};
     const uint64_t strides[1] = {(uint64_t)a.d_in * 2};
     const uint32_t box[2] = {V2_BLOCK_K, BLOCK_N / 2};
     if ((rc = make_tmap_bf16(&tm_w, a.W, 2, dims, strides, box))) return rc;
   }
   if (has_lora) {
     {
-      const uint64_t dims[2] = {(uint64_t)a.d_in, (uint64_t)a.n_adapters * a.r};
+      const uint64_t dims[2] = {(uint64_t)a.d_in, (uint64_t)n_sets * a.n_adapters * a.r};
       const uint64_t strides[1] = {(uint64_t)a.d_in * 2};
       const uint32_t box[2] = {V2_BLOCK_K, (uint32_t)a.r / 2};
       if ((rc = make_tmap_bf16(&tm_a, a.A_stack, 2, dims, strides, box))) return rc;
     }
     {
-      const uint64_t dims[2] = {(uint64_t)SAR_RPAD, (uint64_t)a.n_adapters * a.d_out};
+      const uint64_t dims[2] = {(uint64_t)SAR_RPAD, (uint64_t)n_sets * a.n_adapters * a.d_out};
       const uint64_t strides[1] = {(uint64_t)SAR_RPAD * 2};
       const uint32_t box[2] = {64, BLOCK_N / 2};
       if ((rc = make_tmap_bf16(&tm_b, a.Bp_stack, 2, dims, strides, box))) return rc;
@@ -443,7 +541,7 @@ static int k1v2_launch(const K1Args& a, cudaStream_t stream) {
     if (e != cudaSuccess) return fail_cuda(e, "k1v2: cudaFuncSetAttribute");
     smem_set = dev.max_smem_optin;
   }
-  kern<<<2 * pairs, V2_THREADS, smem_bytes, stream>>>(tm_x, tm_w, tm_a, tm_b, tm_y, p);
+  kern<<<2 * pairs, V2_THREADS, smem_bytes, stream>>>(tm_x, tm_w, tm_a, tm_b, tm_y[0], tm_y[1], tm_y[2], p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail_cuda(e, "k1v2: launch");
   return SAR_OK;
@@ -455,6 +553,26 @@ int k1v2_qv_lora_fwd(const K1Args& a, int block_n, cudaStream_t stream) {
     case 192: return k1v2_launch<192>(a, stream);
     default: return fail(SAR_EINVAL, "k1v2: unsupported BLOCK_N");
   }
+}
+
+// Fused attention-projection entry (sar_attn_proj_fwd): validates and always runs on the pair kernel.
+int attn_proj_fwd(const K1Args& a, cudaStream_t stream) {
+  if (!a.x || !a.W) return fail(SAR_EINVAL, "attn_proj: null x/W");
+  if (a.B <= 0 || a.T <= 0) return fail(SAR_EINVAL, "attn_proj: B and T must be positive");
+  if (a.n_seg < 1 || a.n_seg > 3) return fail(SAR_EINVAL, "attn_proj: n_seg must be 1, 2 or 3");
+  if (a.d_in % 64 || a.d_out % 128 || a.d_in <= 0 || a.d_out <= 0)
+    return fail(SAR_EINVAL, "attn_proj: d_in must be a multiple of 64 and d_out of 128");
+  const bool lora = a.n_adapters > 0 && a.utt_adapter && a.A_stack && a.Bp_stack;
+  if (lora && (a.r % 16 || a.r < 16 || a.r > 64)) return fail(SAR_EINVAL, "attn_proj: r must be 16, 32, 48 or 64");
+  if (lora && (a.n_sets < 1 || a.n_sets > 2)) return fail(SAR_EINVAL, "attn_proj: n_sets must be 1 or 2");
+  uintptr_t al = reinterpret_cast<uintptr_t>(a.x) | reinterpret_cast<uintptr_t>(a.W) |
+                 reinterpret_cast<uintptr_t>(a.A_stack) | reinterpret_cast<uintptr_t>(a.Bp_stack) |
+                 reinterpret_cast<uintptr_t>(a.bias);
+  for (int s = 0; s < a.n_seg; ++s) al |= reinterpret_cast<uintptr_t>(a.y_seg[s]);
+  if (al & 15) return fail(SAR_EINVAL, "attn_proj: pointers must be 16-byte aligned");
+  int bn = a.block_n_override ? a.block_n_override : ((a.d_out % 192 == 0) ? 192 : 128);
+  if (a.d_out % bn) return fail(SAR_EINVAL, "attn_proj: d_out not divisible by BLOCK_N");
+  return k1v2_qv_lora_fwd(a, bn, stream);
 }
 
 }  // namespace sar

@@ -129,6 +129,66 @@ int sar_qv_lora_fwd(const void* x, const void* W, const void* bias, const void* 
   return k1_qv_lora_fwd(a, static_cast<cudaStream_t>(stream));
 }
 
+int sar_attn_proj_fwd(const void* x, int x_head_major, const void* W_cat, const void* bias_cat, const void* A_cat,
+                      const void* Bp_cat, const int32_t* utt_adapter, void* const* y, const int32_t* seg_set,
+                      const float* seg_scale, int n_seg, int n_sets, int y_head_major, int B, int T, int d_in,
+                      int d_out, int r, int n_adapters, float scale, uint32_t flags, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  if (!y || !seg_set || !seg_scale || n_seg < 1 || n_seg > 3) return fail(SAR_EINVAL, "sar_attn_proj_fwd: bad segments");
+  K1Args a{};
+  a.x = x; a.W = W_cat; a.bias = bias_cat; a.A_stack = A_cat; a.Bp_stack = Bp_cat; a.utt_adapter = utt_adapter;
+  a.B = B; a.T = T; a.d_in = d_in; a.d_out = d_out; a.r = r; a.n_adapters = n_adapters; a.scale = scale;
+  a.block_n_override = static_cast<int>((flags >> 8) & 0x3FF);
+  a.grid_override = static_cast<int>((flags >> 18) & 0x3FF);
+  a.n_seg = n_seg; a.n_sets = n_sets; a.x_head_major = x_head_major; a.y_head_major = y_head_major;
+  for (int s = 0; s < n_seg; ++s) {
+    a.seg_set[s] = seg_set[s];
+    a.seg_scale[s] = seg_scale[s];
+    a.y_seg[s] = y[s];
+  }
+  for (int s = n_seg; s < 3; ++s) {
+    a.seg_set[s] = -1;
+    a.seg_scale[s] = 1.0f;
+  }
+  return attn_proj_fwd(a, static_cast<cudaStream_t>(stream));
+}
+
+int sar_qv_lora_fwd_pair(const void* x, const void* W_cat, const void* bias_cat, const void* A_cat,
+                         const void* Bp_cat, const int32_t* utt_adapter, void* y_q, void* y_v, int B, int T, int d_in,
+                         int d_out, int r, int n_adapters, float scale, uint32_t flags, void* stream) {
+  void* ys[2] = {y_q, y_v};
+  const int32_t sets[2] = {0, 1};
+  const float scales[2] = {1.0f, 1.0f};
+  return sar_attn_proj_fwd(x, 0, W_cat, bias_cat, A_cat, Bp_cat, utt_adapter, ys, sets, scales, 2, 2, 0, B, T, d_in,
+                           d_out, r, n_adapters, scale, flags, stream);
+}
+
+int sar_linear_fwd(const void* x, int x_head_major, const void* W, const void* bias, const void* residual, void* y,
+                   int B, int T, int d_in, int d_out, int act, uint32_t flags, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  if (act != SAR_ACT_NONE && act != SAR_ACT_GELU) return fail(SAR_EINVAL, "sar_linear_fwd: unknown activation");
+  if (reinterpret_cast<uintptr_t>(residual) & 15) return fail(SAR_EINVAL, "sar_linear_fwd: residual must be 16-byte aligned");
+  K1Args a{};
+  a.x = x; a.W = W; a.bias = bias; a.B = B; a.T = T; a.d_in = d_in; a.d_out = d_out; a.r = 16; a.scale = 0.f;
+  a.block_n_override = static_cast<int>((flags >> 8) & 0x3FF);
+  a.grid_override = static_cast<int>((flags >> 18) & 0x3FF);
+  a.n_seg = 1; a.n_sets = 1; a.x_head_major = x_head_major; a.y_head_major = 0;
+  a.seg_set[0] = a.seg_set[1] = a.seg_set[2] = -1;
+  a.seg_scale[0] = a.seg_scale[1] = a.seg_scale[2] = 1.0f;
+  a.y_seg[0] = y;
+  a.residual = residual; a.act = act;
+  return attn_proj_fwd(a, static_cast<cudaStream_t>(stream));
+}
+
+int sar_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, int64_t M, int d, float eps,
+                      void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  return layernorm_fwd(x, gamma, beta, y, M, d, eps, static_cast<cudaStream_t>(stream));
+}
+
 int sar_qv_lora_fwd_rows(const void* x, const void* W, const void* bias, const void* A_stack, const void* Bp_stack,
                          const int32_t* row_adapter, void* y, int M, int d_in, int d_out, int r, int n_adapters,
                          float scale, void* ws, void* stream) {

@@ -48,9 +48,22 @@ struct K1Args {
   int grid_override;     // 0 = auto
   int kernel_override;   // 0 = auto, 1 = single-CTA kernel, 2 = CTA-pair (cta_group::2) kernel
   int swap_halves;       // debug switch of the pair kernel's B-operand half assignment
+  // ---- fused attention-projection extensions (pair kernel only); n_seg == 0 means "plain single projection"
+  int n_seg;             // output segments sharing x (W, bias concatenated along d_out): q|k|v = 3, k|v = 2
+  int n_sets;            // LoRA sets stacked in A_stack / Bp_stack ([n_sets*n_adapters, ...])
+  int seg_set[3];        // LoRA set per segment (-1 = none)
+  float seg_scale[3];    // epilogue scale per segment
+  void* y_seg[3];        // one output tensor per segment
+  int x_head_major;      // x is [B, d_in/64, T, 64]
+  int y_head_major;      // every y is [B, d_out/64, T, 64]
+  const void* residual;  // bf16 [B, T, d_out] added in the epilogue (single row-major segment only)
+  int act;               // SAR_ACT_*
 };
 int k1_qv_lora_fwd(const K1Args& a, cudaStream_t stream);
 int k1v2_qv_lora_fwd(const K1Args& a, int block_n, cudaStream_t stream);
+int attn_proj_fwd(const K1Args& a, cudaStream_t stream);
+int layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, int64_t M, int d, float eps,
+                  cudaStream_t stream);
 
 struct K2Args {
   const void* h;

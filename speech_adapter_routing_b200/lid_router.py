@@ -230,6 +230,8 @@ class EncoderFeatureExtractor(nn.Module):
         self.layer_index = layer_index
         for p in self.model.parameters():
             p.requires_grad = False
+        from .whisper_blocks import install_fused_blocks
+        install_fused_blocks(self.model)
 
     def _get_encoder(self) -> nn.Module:
         try:

@@ -164,6 +164,20 @@ class RoutedLoRALinear(nn.Module):
             self._cache[ck] = t
         return t
 
+    def resolve_index(self, B: int, device) -> Optional[torch.Tensor]:
+        """int32 [B] adapter index per utterance for this call: the routing context if one is active, else the
+        module's active adapter for every utterance; None = base weights only."""
+        idx = current_utt_adapter()
+        if idx is None:
+            return self._default_index(B, device)
+        if self.disable_adapters or not self.adapter_order:
+            return None
+        if idx.numel() != B:
+            if B % idx.numel():
+                raise ValueError(f"routing context has {idx.numel()} utterances but the batch has {B}")
+            idx = idx.repeat_interleave(B // idx.numel())   # beam search expands the batch
+        return idx
+
     # ------------------------------------------------------------------ forward
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         if not x.is_cuda:
@@ -180,15 +194,7 @@ class RoutedLoRALinear(nn.Module):
         if x3.dtype != torch.bfloat16:
             x3 = x3.to(torch.bfloat16)
         B, T = x3.shape[0], x3.shape[1]
-        idx = current_utt_adapter()
-        if idx is None:
-            idx = self._default_index(B, x3.device)
-        elif self.disable_adapters or not self.adapter_order:
-            idx = None
-        elif idx.numel() != B:
-            if B % idx.numel():
-                raise ValueError(f"routing context has {idx.numel()} utterances but the batch has {B}")
-            idx = idx.repeat_interleave(B // idx.numel())   # beam search expands the batch
+        idx = self.resolve_index(B, x3.device)
         if self.training and idx is not None:
             name = self.active_adapter
             if isinstance(self.lora_dropout[name], nn.Dropout) and self.lora_dropout[name].p > 0:

@@ -4,7 +4,8 @@ the tensors are not CUDA tensors — there is no eager fallback.
 """
 from __future__ import annotations
 
-from typing import NamedTuple, Optional, Tuple
+import ctypes
+from typing import List, NamedTuple, Optional, Sequence, Tuple
 
 import torch
 
@@ -13,7 +14,7 @@ from ._lib import SAR_FLAG_SAVE_U, SAR_RPAD, check, lib
 
 
 # ---- instrumentation used by bench.py: kernel-launch counts and (optional) per-launch CUDA-event timing ----------
-LAUNCHES = {"k1": 0, "k2": 0, "k3": 0, "rows": 0}   # kernels launched by libsar, by op (k2 = 2, k3 = 3, rows = 2)
+LAUNCHES = {"k1": 0, "k2": 0, "k3": 0, "rows": 0, "proj": 0, "linear": 0, "ln": 0}   # kernels launched by libsar, by op (k2 = 2, k3 = 3, rows = 2)
 K1_TIMELINE = None   # set to a list to record (B*T, d_in, d_out, r, has_lora, start_event, end_event) per K1 call
 
 
@@ -94,19 +95,126 @@ def qv_lora_fwd(x: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], 
     u = torch.empty(B * T, r, dtype=torch.bfloat16, device=x.device) if (save_u and n_adapters) else None
     flags = ((SAR_FLAG_SAVE_U if u is not None else 0) | ((block_n & 0x3FF) << 8) | ((grid & 0x3FF) << 18) |
              ((kernel & 0x3) << 28) | (2 if swap_halves else 0))
-    tl = K1_TIMELINE
-    if tl is not None:
-        ev0 = torch.cuda.Event(enable_timing=True)
-        ev1 = torch.cuda.Event(enable_timing=True)
-        ev0.record()
-    check(lib().sar_qv_lora_fwd(_ptr(x), _ptr(W), _ptr(bias), _ptr(A_stack), _ptr(Bp_stack),
-                                _ptr(utt_adapter) if n_adapters else None, _ptr(y), _ptr(u), B, T, d_in, d_out, r,
-                                n_adapters, float(scale), flags, _stream(x)))
-    if tl is not None:
-        ev1.record()
-        tl.append((B * T, d_in, d_out, r, n_adapters > 0, ev0, ev1))
+    def launch():
+        check(lib().sar_qv_lora_fwd(_ptr(x), _ptr(W), _ptr(bias), _ptr(A_stack), _ptr(Bp_stack),
+                                    _ptr(utt_adapter) if n_adapters else None, _ptr(y), _ptr(u), B, T, d_in, d_out, r,
+                                    n_adapters, float(scale), flags, _stream(x)))
+    flops = 2.0 * B * T * d_in * d_out + (2.0 * B * T * r * (d_in + d_out) if n_adapters else 0.0)
+    _time_k1(K1_TIMELINE, "k1", B * T, d_in, d_out, flops, launch)
     LAUNCHES["k1"] += 1
     return y, u
+
+
+def _time_k1(tl, kind, M, d_in, d_out, flops, fn):
+    """Run ``fn`` (one tcgen05 GEMM launch) bracketed by CUDA events when bench.py asked for a timeline.
+    ``flops`` = ALGORITHMIC flops of the call: 2·M·d_in·d_out + 2·M·r·(d_in + d_out) per LoRA'd segment."""
+    if tl is None:
+        fn()
+        return
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    fn()
+    ev1.record()
+    tl.append((kind, M, d_in, d_out, flops, ev0, ev1))
+
+
+def attn_proj_fwd(x: torch.Tensor, W_cat: torch.Tensor, bias_cat: Optional[torch.Tensor],
+                  A_cat: Optional[torch.Tensor], Bp_cat: Optional[torch.Tensor], utt_adapter: Optional[torch.Tensor],
+                  seg_set: Sequence[int], seg_scale: Sequence[float], n_sets: int, scale: float,
+                  x_head_major: bool = False, y_head_major: bool = True, block_n: int = 0,
+                  grid: int = 0) -> List[torch.Tensor]:
+    """Fused attention projections (sar_attn_proj_fwd): up to three projections of the same x in one launch.
+
+    x [B,T,d_in] (or [B,d_in/64,T,64] if ``x_head_major``); W_cat [n_seg*d_out, d_in]; A_cat [n_sets*n, r, d_in];
+    Bp_cat [n_sets*n, d_out, 64].  Returns n_seg tensors, [B,d_out/64,T,64] if ``y_head_major`` else [B,T,d_out].
+    """
+    _need_cuda(x, W_cat, bias_cat, A_cat, Bp_cat, utt_adapter)
+    x = _bf16c(x, "x"); W_cat = _bf16c(W_cat, "W_cat"); bias_cat = _bf16c(bias_cat, "bias_cat")
+    A_cat = _bf16c(A_cat, "A_cat"); Bp_cat = _bf16c(Bp_cat, "Bp_cat")
+    n_seg = len(seg_set)
+    if x_head_major:
+        B, hh, T, hd = x.shape
+        d_in = hh * hd
+    else:
+        B, T, d_in = x.shape
+    if W_cat.shape[1] != d_in or W_cat.shape[0] % n_seg:
+        raise ValueError("W_cat must be [n_seg*d_out, d_in]")
+    d_out = W_cat.shape[0] // n_seg
+    n_adapters, r = 0, 16
+    if A_cat is not None and utt_adapter is not None and any(s >= 0 for s in seg_set):
+        if A_cat.shape[0] % n_sets:
+            raise ValueError("A_cat must be [n_sets*n_adapters, r, d_in]")
+        n_adapters, r = A_cat.shape[0] // n_sets, A_cat.shape[1]
+        if A_cat.shape[2] != d_in or tuple(Bp_cat.shape) != (n_sets * n_adapters, d_out, SAR_RPAD):
+            raise ValueError("A_cat must be [n_sets*n,r,d_in] and Bp_cat [n_sets*n,d_out,64]")
+        if utt_adapter.dtype != torch.int32 or utt_adapter.numel() != B:
+            raise ValueError("utt_adapter must be int32 [B]")
+        utt_adapter = utt_adapter.contiguous()
+    if y_head_major:
+        if d_out % 64:
+            raise ValueError("head-major output needs d_out % 64 == 0")
+        ys = [torch.empty(B, d_out // 64, T, 64, dtype=torch.bfloat16, device=x.device) for _ in range(n_seg)]
+    else:
+        ys = [torch.empty(B, T, d_out, dtype=torch.bfloat16, device=x.device) for _ in range(n_seg)]
+    yp = (ctypes.c_void_p * n_seg)(*[y.data_ptr() for y in ys])
+    ss = (ctypes.c_int32 * n_seg)(*[int(s) for s in seg_set])
+    sc = (ctypes.c_float * n_seg)(*[float(s) for s in seg_scale])
+    flags = ((block_n & 0x3FF) << 8) | ((grid & 0x3FF) << 18)
+    has_lora = n_adapters > 0
+
+    def launch():
+        check(lib().sar_attn_proj_fwd(_ptr(x), int(x_head_major), _ptr(W_cat), _ptr(bias_cat),
+                                      _ptr(A_cat) if has_lora else None, _ptr(Bp_cat) if has_lora else None,
+                                      _ptr(utt_adapter) if has_lora else None, yp, ss, sc, n_seg,
+                                      n_sets if has_lora else 1, int(y_head_major), B, T, d_in, d_out, r, n_adapters,
+                                      float(scale), flags, _stream(x)))
+    n_lora = sum(1 for s in seg_set if s >= 0) if has_lora else 0
+    flops = 2.0 * B * T * d_in * d_out * n_seg + 2.0 * B * T * r * (n_sets * d_in + n_lora * d_out) * (n_lora > 0)
+    _time_k1(K1_TIMELINE, "proj", B * T, d_in, n_seg * d_out, flops, launch)
+    LAUNCHES["proj"] += 1
+    return ys
+
+
+def linear_fwd(x: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], residual: Optional[torch.Tensor] = None,
+               act: int = _lib.SAR_ACT_NONE, x_head_major: bool = False, out: Optional[torch.Tensor] = None,
+               block_n: int = 0, grid: int = 0) -> torch.Tensor:
+    """y = act(x·Wᵀ + bias) + residual on the tcgen05 pair kernel (sar_linear_fwd).  x [B,T,d_in] or head-major
+    [B,d_in/64,T,64]; residual / y [B,T,d_out] (``out`` may be the residual tensor: in-place residual update)."""
+    _need_cuda(x, W, bias, residual)
+    x = _bf16c(x, "x"); W = _bf16c(W, "W"); bias = _bf16c(bias, "bias"); residual = _bf16c(residual, "residual")
+    if x_head_major:
+        B, hh, T, hd = x.shape
+        d_in = hh * hd
+    else:
+        B, T, d_in = x.shape
+    d_out = W.shape[0]
+    if W.shape[1] != d_in:
+        raise ValueError("W must be [d_out, d_in]")
+    if residual is not None and tuple(residual.shape) != (B, T, d_out):
+        raise ValueError("residual must be [B, T, d_out]")
+    y = out if out is not None else torch.empty(B, T, d_out, dtype=torch.bfloat16, device=x.device)
+    flags = ((block_n & 0x3FF) << 8) | ((grid & 0x3FF) << 18)
+
+    def launch():
+        check(lib().sar_linear_fwd(_ptr(x), int(x_head_major), _ptr(W), _ptr(bias), _ptr(residual), _ptr(y), B, T,
+                                   d_in, d_out, int(act), flags, _stream(x)))
+    _time_k1(K1_TIMELINE, "linear", B * T, d_in, d_out, 2.0 * B * T * d_in * d_out, launch)
+    LAUNCHES["linear"] += 1
+    return y
+
+
+def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """LayerNorm over the last dim (sar_layernorm_fwd): bf16 in/out, fp32 statistics."""
+    _need_cuda(x, gamma, beta)
+    x = _bf16c(x, "x"); gamma = _bf16c(gamma, "gamma"); beta = _bf16c(beta, "beta")
+    d = x.shape[-1]
+    M = x.numel() // d
+    y = out if out is not None else torch.empty_like(x)
+    check(lib().sar_layernorm_fwd(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), M, d, float(eps), _stream(x)))
+    LAUNCHES["ln"] += 1
+    return y
 
 
 def qv_lora_fwd_rows(x: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], A_stack: Optional[torch.Tensor],

@@ -91,6 +91,8 @@ def inject_lora(model: nn.Module, config: LoraConfig, adapter_name: str = "defau
             hit.append(name)
     if not hit:
         raise ValueError(f"target_modules {targets} matched no nn.Linear in the model")
+    from .whisper_blocks import install_fused_blocks
+    install_fused_blocks(model)   # (re)bind the fused Whisper block bodies over the new q_proj / v_proj modules
     return hit
 
 

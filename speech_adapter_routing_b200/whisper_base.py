@@ -106,6 +106,8 @@ def load_base_model(model_name: str, device: Optional[str] = None, dtype: Option
         model.generation_config.forced_decoder_ids = None
         model.generation_config.suppress_tokens = []
     model.to(device)
+    from .whisper_blocks import install_fused_blocks
+    install_fused_blocks(model)
     logger.info("Loaded model with %.1fM parameters", sum(p.numel() for p in model.parameters()) / 1e6)
     return model
 

@@ -197,6 +197,165 @@ def suite_k3():
     return ok
 
 
+def _hm(y):   # [B,h,T,64] -> [B,T,h*64]
+    B, h, T, e = y.shape
+    return y.permute(0, 2, 1, 3).reshape(B, T, h * e)
+
+
+def run_proj_case(name, B, T, d, r, n, segs, grid=0, block_n=0, seed=4321, base_only_every=0):
+    """segs: list of (lora: bool, scale) in output order; every LoRA'd segment is its own set."""
+    cases = [fixtures.make_lora_case(B, T, d, d, r, max(n, 1), seed=seed + 10 * i, base_only_every=base_only_every)
+             for i in range(len(segs))]
+    x = cases[0].x
+    idx = cases[0].utt_adapter
+    none = torch.full((B,), -1, dtype=torch.int32)
+    refs, seg_set, As, Bps = [], [], [], []
+    for (lora, sc), c in zip(segs, cases):
+        ref = olora.lora_linear_routed_k1_rounding(x, c.W, c.bias, c.A_stack, c.B_stack, c.scaling, idx if lora else none)
+        refs.append((ref.float() * sc))
+        if lora:
+            seg_set.append(len(As)); As.append(c.A_stack); Bps.append(ops.pack_lora_b(c.B_stack))
+        else:
+            seg_set.append(-1)
+    W = torch.cat([c.W for c in cases], 0).to(DEV)
+    bias = torch.cat([c.bias for c in cases], 0).to(DEV)
+    A = torch.cat(As, 0).to(DEV) if As else None
+    Bp = torch.cat(Bps, 0).to(DEV) if As else None
+    ok = True
+    for hm in (True, False):
+        ys = ops.attn_proj_fwd(x.to(DEV), W, bias, A, Bp, idx.to(DEV) if As else None, seg_set, [s for _, s in segs],
+                               max(len(As), 1), 2.0, y_head_major=hm, grid=grid, block_n=block_n)
+        torch.cuda.synchronize()
+        rels = []
+        for y, ref in zip(ys, refs):
+            yy = _hm(y) if hm else y
+            _, rel, _ = err_stats(yy, ref)
+            rels.append(rel)
+        good = max(rels) < 2e-2
+        ok &= good
+        log(f"[proj] {name:34s} B={B} T={T} d={d} r={r} n={n} segs={len(segs)} head_major={hm}: rel={['%.3g' % r_ for r_ in rels]} "
+            f"{'OK' if good else 'FAIL'}")
+    return ok
+
+
+def suite_proj():
+    ok = True
+    s = 0.125
+    ok &= run_proj_case("q only (cross-attn q)", 3, 300, 768, 16, 4, [(True, s)])
+    ok &= run_proj_case("k|v (cross-attn kv)", 3, 300, 768, 16, 4, [(False, 1.0), (True, 1.0)])
+    ok &= run_proj_case("q|k|v self-attn", 3, 300, 768, 16, 4, [(True, s), (False, 1.0), (True, 1.0)])
+    ok &= run_proj_case("q|k|v base only (no adapters)", 2, 256, 768, 16, 0, [(False, s), (False, 1.0), (False, 1.0)])
+    ok &= run_proj_case("q|k|v mid-unit ranges", 3, 256, 768, 16, 4, [(True, s), (False, 1.0), (True, 1.0)], grid=10)
+    ok &= run_proj_case("q|k|v 1 pair serial", 3, 260, 768, 16, 4, [(True, s), (False, 1.0), (True, 1.0)], grid=2)
+    ok &= run_proj_case("q|k|v base-only utts", 6, 200, 768, 16, 4, [(True, s), (False, 1.0), (True, 1.0)], base_only_every=3)
+    ok &= run_proj_case("q|k|v r32 d1024", 4, 200, 1024, 32, 4, [(True, s), (False, 1.0), (True, 1.0)])
+    ok &= run_proj_case("q|k|v r64 d1280", 4, 130, 1280, 64, 8, [(True, s), (False, 1.0), (True, 1.0)])
+    ok &= run_proj_case("q|k|v T=1500 B=8", 8, 1500, 768, 16, 4, [(True, s), (False, 1.0), (True, 1.0)])
+    ok &= run_proj_case("q|k|v T=128 (decoder)", 8, 128, 768, 16, 4, [(True, s), (False, 1.0), (True, 1.0)])
+    ok &= run_proj_case("q|k|v d=384 (tiny)", 4, 100, 384, 16, 2, [(True, s), (False, 1.0), (True, 1.0)])
+    log("[proj] suite", "PASSED" if ok else "FAILED")
+    return ok
+
+
+def suite_linear():
+    ok = True
+    g = torch.Generator().manual_seed(11)
+    for (name, B, T, d_in, d_out, act, res, hm, grid) in [
+            ("plain", 2, 300, 768, 768, 0, False, False, 0),
+            ("fc1 + GELU", 2, 300, 768, 3072, 1, False, False, 0),
+            ("fc2 + residual (K=3072)", 2, 300, 3072, 768, 0, True, False, 0),
+            ("out_proj head-major + residual", 3, 300, 768, 768, 0, True, True, 0),
+            ("out_proj head-major mid-unit", 3, 256, 768, 768, 0, True, True, 10),
+            ("flattened [1, B*T]", 1, 8192, 768, 3072, 1, False, False, 0),
+            ("d=1280 ffn 5120 GELU", 2, 200, 1280, 5120, 1, False, False, 0),
+            ("d=1024 fc2 residual", 2, 200, 4096, 1024, 0, True, False, 0),
+            ("in-place residual", 2, 300, 768, 768, 0, True, False, 0)]:
+        x = torch.randn(B, T, d_in, generator=g).to(torch.bfloat16)
+        W = (torch.randn(d_out, d_in, generator=g) * 0.02).to(torch.bfloat16)
+        b = (torch.randn(d_out, generator=g) * 0.02).to(torch.bfloat16)
+        r = torch.randn(B, T, d_out, generator=g).to(torch.bfloat16) if res else None
+        ref = torch.nn.functional.linear(x.float(), W.float(), b.float())
+        if act:
+            ref = torch.nn.functional.gelu(ref)
+        if res:
+            ref = ref + r.float()
+        xd = x.to(DEV)
+        if hm:
+            xd = xd.view(B, T, d_in // 64, 64).permute(0, 2, 1, 3).contiguous()
+        rd = None if r is None else r.to(DEV)
+        inplace = name.startswith("in-place")
+        y = ops.linear_fwd(xd, W.to(DEV), b.to(DEV), rd, act, x_head_major=hm, out=rd if inplace else None, grid=grid)
+        torch.cuda.synchronize()
+        mx, rel, _ = err_stats(y, ref)
+        good = rel < 1e-2
+        ok &= good
+        log(f"[linear] {name:34s} B={B} T={T} {d_in}->{d_out}: max_abs={mx:.4g} rel={rel:.3g} {'OK' if good else 'FAIL'}")
+    log("[linear] suite", "PASSED" if ok else "FAILED")
+    return ok
+
+
+def suite_ln():
+    ok = True
+    g = torch.Generator().manual_seed(12)
+    for (M, d) in [(7, 64), (1000, 384), (3000, 768), (96000, 768), (515, 1024), (300, 1280), (33, 2048)]:
+        x = (torch.randn(M, d, generator=g) * 2 + 0.5).to(torch.bfloat16)
+        w = (1 + 0.1 * torch.randn(d, generator=g)).to(torch.bfloat16)
+        b = (0.1 * torch.randn(d, generator=g)).to(torch.bfloat16)
+        ref = torch.nn.functional.layer_norm(x.float(), (d,), w.float(), b.float(), 1e-5)
+        y = ops.layernorm_fwd(x.to(DEV), w.to(DEV), b.to(DEV), 1e-5)
+        torch.cuda.synchronize()
+        mx, rel, _ = err_stats(y, ref)
+        good = mx < 0.04   # one bf16 rounding of values up to ~5
+        ok &= good
+        log(f"[ln] M={M} d={d}: max_abs={mx:.4g} rel={rel:.3g} {'OK' if good else 'FAIL'}")
+    log("[ln] suite", "PASSED" if ok else "FAILED")
+    return ok
+
+
+def suite_blocks():
+    """Fused Whisper blocks vs HF's own layer bodies (same RoutedLoRALinear modules) on a small geometry."""
+    import speech_adapter_routing_b200 as sar
+    from speech_adapter_routing_b200 import whisper_blocks
+    from transformers import WhisperConfig, WhisperForConditionalGeneration
+
+    cfg = WhisperConfig(vocab_size=1000, num_mel_bins=80, d_model=384, encoder_layers=2, decoder_layers=2,
+                        encoder_attention_heads=6, decoder_attention_heads=6, encoder_ffn_dim=1536,
+                        decoder_ffn_dim=1536, max_source_positions=1500, max_target_positions=448,
+                        pad_token_id=0, bos_token_id=1, eos_token_id=2, decoder_start_token_id=3)
+    torch.manual_seed(0)
+    model = WhisperForConditionalGeneration(cfg).to(torch.bfloat16).to(DEV).eval()
+    lcfg = sar.LoraConfig(r=16, lora_alpha=32, target_modules=["q_proj", "v_proj"])
+    langs = ["a", "b", "c"]
+    for l in langs:
+        sar.inject_lora(model, lcfg, adapter_name=l)
+    g = torch.Generator().manual_seed(3)
+    for m in sar.lora_modules(model).values():
+        for l in langs:
+            m.lora_B[l].weight.data.copy_((torch.randn(m.out_features, 16, generator=g) * 0.05).to(DEV))
+    B = 5
+    x = torch.randn(B, 80, 3000, generator=g).to(torch.bfloat16).to(DEV)
+    dec = torch.randint(4, 1000, (B, 37), generator=g).to(DEV)
+    idx = torch.tensor([0, 2, -1, 1, 2], dtype=torch.int32, device=DEV)
+    ok = True
+    with torch.no_grad(), sar.route(idx):
+        ops.reset_counters()
+        y1 = model(input_features=x, decoder_input_ids=dec, use_cache=False).logits.float()
+        fused_counts = dict(ops.LAUNCHES)
+        whisper_blocks.FUSED_BLOCKS_ENABLED = False
+        ops.reset_counters()
+        y0 = model(input_features=x, decoder_input_ids=dec, use_cache=False).logits.float()
+        hf_counts = dict(ops.LAUNCHES)
+        whisper_blocks.FUSED_BLOCKS_ENABLED = True
+    rel = ((y1 - y0).abs().max() / y0.abs().max()).item()
+    same = (y1.argmax(-1) == y0.argmax(-1)).float().mean().item()
+    good = rel < 3e-2 and fused_counts["proj"] > 0 and hf_counts["proj"] == 0
+    ok &= good
+    log(f"[blocks] fused vs HF bodies: rel={rel:.3g} argmax agreement={same:.4f} launches fused={fused_counts} hf={hf_counts} "
+        f"{'OK' if good else 'FAIL'}")
+    log("[blocks] suite", "PASSED" if ok else "FAILED")
+    return ok
+
+
 def timeit(fn, iters=20, warmup=3):
     for _ in range(warmup):
         fn()
@@ -249,6 +408,66 @@ def suite_perf():
         p = ops.RouterParams.from_state_dict(sd, DEV)
         ms = timeit(lambda: ops.router_fwd(xs[it[0] % nbuf], p))
         log(f"[perf] k2 router d={d}: {ms*1e3:.1f} us  {B*T*d*2/ms/1e6:.1f} GB/s (includes alloc + 2 launches)")
+
+
+def suite_perf2():
+    """Whisper-block GEMMs / LN / SDPA at the bench shape (B=64, T=1500)."""
+    import torch.nn.functional as F
+    for (d, ffn, r, n) in [(768, 3072, 16, 4), (1280, 5120, 64, 8)]:
+        B, T = 64, 1500
+        g = torch.Generator().manual_seed(1)
+        nbuf = 3
+        xs = [torch.randn(B, T, d, device=DEV, dtype=torch.bfloat16) for _ in range(nbuf)]
+        Wqkv = (torch.randn(3 * d, d, device=DEV) * 0.02).to(torch.bfloat16)
+        bqkv = torch.zeros(3 * d, device=DEV, dtype=torch.bfloat16)
+        A = (torch.randn(2 * n, r, d, device=DEV) * 0.03).to(torch.bfloat16)
+        Bp = ops.pack_lora_b((torch.randn(2 * n, d, r, device=DEV) * 0.02).to(torch.bfloat16))
+        ia = torch.randint(0, n, (B,), generator=g).to(torch.int32).to(DEV)
+        it = [0]
+
+        def nxt():
+            it[0] += 1
+            return it[0] % nbuf
+        fl_qkv = 2.0 * B * T * d * 3 * d + 2.0 * B * T * r * 4 * d
+        ms = timeit(lambda: ops.attn_proj_fwd(xs[nxt()], Wqkv, bqkv, A, Bp, ia, [0, -1, 1], [0.125, 1, 1], 2, 2.0))
+        log(f"[perf2] d={d} qkv+lora fused head-major: {ms*1e3:.1f} us  {fl_qkv/ms/1e9:.1f} TFLOP/s")
+        ms = timeit(lambda: ops.attn_proj_fwd(xs[nxt()], Wqkv, bqkv, None, None, None, [-1, -1, -1], [0.125, 1, 1], 1, 2.0))
+        log(f"[perf2] d={d} qkv base fused head-major: {ms*1e3:.1f} us  {2.0*B*T*d*3*d/ms/1e9:.1f} TFLOP/s")
+        W1 = (torch.randn(ffn, d, device=DEV) * 0.02).to(torch.bfloat16); b1 = torch.zeros(ffn, device=DEV, dtype=torch.bfloat16)
+        W2 = (torch.randn(d, ffn, device=DEV) * 0.02).to(torch.bfloat16); b2 = torch.zeros(d, device=DEV, dtype=torch.bfloat16)
+        Wo = (torch.randn(d, d, device=DEV) * 0.02).to(torch.bfloat16)
+        fs = [torch.randn(1, B * T, ffn, device=DEV, dtype=torch.bfloat16) for _ in range(2)]
+        x1 = [x.view(1, B * T, d) for x in xs]
+        ms = timeit(lambda: ops.linear_fwd(x1[nxt()], W1, b1, None, 1, out=fs[it[0] % 2]))
+        log(f"[perf2] d={d} fc1+GELU: {ms*1e3:.1f} us  {2.0*B*T*d*ffn/ms/1e9:.1f} TFLOP/s")
+        ms = timeit(lambda: ops.linear_fwd(x1[nxt()], W1, b1, None, 0, out=fs[it[0] % 2]))
+        log(f"[perf2] d={d} fc1 (no act): {ms*1e3:.1f} us  {2.0*B*T*d*ffn/ms/1e9:.1f} TFLOP/s")
+        ms = timeit(lambda: ops.linear_fwd(fs[nxt() % 2], W2, b2, x1[it[0] % nbuf], 0, out=x1[it[0] % nbuf]))
+        log(f"[perf2] d={d} fc2+residual: {ms*1e3:.1f} us  {2.0*B*T*d*ffn/ms/1e9:.1f} TFLOP/s")
+        ms = timeit(lambda: F.linear(fs[nxt() % 2], W2, b2))
+        log(f"[perf2] d={d} cuBLAS fc2: {ms*1e3:.1f} us  {2.0*B*T*d*ffn/ms/1e9:.1f} TFLOP/s")
+        hm = [x.view(B, d // 64, T, 64) for x in xs]
+        ms = timeit(lambda: ops.linear_fwd(hm[nxt()], Wo, b2, xs[(it[0] + 1) % nbuf], 0, x_head_major=True))
+        log(f"[perf2] d={d} out_proj head-major+residual: {ms*1e3:.1f} us  {2.0*B*T*d*d/ms/1e9:.1f} TFLOP/s")
+        gw = torch.ones(d, device=DEV, dtype=torch.bfloat16); gb = torch.zeros(d, device=DEV, dtype=torch.bfloat16)
+        ys = [torch.empty_like(x) for x in xs]
+        ms = timeit(lambda: ops.layernorm_fwd(xs[nxt()], gw, gb, 1e-5, out=ys[it[0] % nbuf]))
+        log(f"[perf2] d={d} layernorm: {ms*1e3:.1f} us  {4.0*B*T*d/ms/1e6:.1f} GB/s")
+        ms = timeit(lambda: F.layer_norm(xs[nxt()], (d,), gw, gb, 1e-5))
+        log(f"[perf2] d={d} torch layernorm: {ms*1e3:.1f} us  {4.0*B*T*d/ms/1e6:.1f} GB/s")
+        fl_att = 4.0 * B * T * T * d
+        from torch.nn.attention import SDPBackend, sdpa_kernel
+        for name, be in (("default", None), ("flash", SDPBackend.FLASH_ATTENTION), ("cudnn", SDPBackend.CUDNN_ATTENTION),
+                         ("efficient", SDPBackend.EFFICIENT_ATTENTION)):
+            try:
+                if be is None:
+                    ms = timeit(lambda: F.scaled_dot_product_attention(hm[nxt()], hm[(it[0] + 1) % nbuf], hm[(it[0] + 2) % nbuf], scale=1.0), iters=5)
+                else:
+                    with sdpa_kernel([be]):
+                        ms = timeit(lambda: F.scaled_dot_product_attention(hm[nxt()], hm[(it[0] + 1) % nbuf], hm[(it[0] + 2) % nbuf], scale=1.0), iters=5)
+                log(f"[perf2] d={d} SDPA {name}: {ms*1e3:.1f} us  {fl_att/ms/1e9:.1f} TFLOP/s")
+            except Exception as e:  # noqa: BLE001
+                log(f"[perf2] d={d} SDPA {name}: unavailable ({type(e).__name__}: {str(e)[:80]})")
 
 
 if __name__ == "__main__":
