@@ -298,26 +298,35 @@ def run_b200_arm(args):
     ms_step = t.item() / args.steps
     value = world * B / (ms_step * 1e-3)
 
-    # ---- roofline of the dominant kernel: K1 at the encoder-row shape (M = B*1500) --------------------------
+    # ---- roofline of the dominant kernel: the tcgen05 pair kernel at the fused q|k|v + routed-LoRA call of the routed
+    # pass's encoder layers (M = B*1500 rows, N = 3d), timed by CUDA events around every launch inside the timed region
     peaks, peak_src = load_peaks()
     M_big = B * 1500
+    d = cfg.d_model
     fl, ms_k1, n_big = 0.0, 0.0, 0
-    ms_k1_all = 0.0
-    for (M, d_in, d_out, r, has_lora, a, b) in timeline:
+    by_kind = {}
+    ms_gemm_all = 0.0
+    for (kind, M, d_in, d_out, flops, a, b) in timeline:
         dt = a.elapsed_time(b)
-        ms_k1_all += dt
-        if M == M_big:
-            fl += 2.0 * M * d_in * d_out + (2.0 * M * r * (d_in + d_out) if has_lora else 0.0)
+        ms_gemm_all += dt
+        lora = flops > 2.0 * M * d_in * d_out
+        key = f"{kind} M={M} {d_in}->{d_out}" + (" +lora" if lora else "")
+        k = by_kind.setdefault(key, [0, 0.0, 0.0])
+        k[0] += 1; k[1] += dt; k[2] += flops
+        if kind == "proj" and M == M_big and d_out == 3 * d and lora:
+            fl += flops
             ms_k1 += dt
             n_big += 1
     achieved = fl / (ms_k1 * 1e-3) / 1e12 if ms_k1 > 0 else 0.0
     peak = float(peaks.get("bf16_tflops_sustained", FALLBACK_PEAKS["bf16_tflops_sustained"]))
-    roofline = {"bound": "tensor", "kernel": "k1_qv_lora_fwd_kernel (M=%d, d=%d)" % (M_big, cfg.d_model),
+    roofline = {"bound": "tensor", "kernel": "k1v2_kernel<192> fused q|k|v + routed LoRA (M=%d, %d->%d, r=%d)" % (M_big, d, 3 * d, RANK_R),
                 "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
                 "traffic": K1_DRAM_TRAFFIC_BYTES, "peak_source": peak_src + ", sustained bf16 (kernel timed inside a long step)",
                 "launches_timed": n_big, "avg_launch_us": 1e3 * ms_k1 / max(n_big, 1),
-                "k1_share_of_step": ms_k1_all / ms_total if ms_total else None,
-                "algorithmic_flops_per_launch": fl / max(n_big, 1)}
+                "gemm_share_of_step": ms_gemm_all / ms_total if ms_total else None,
+                "algorithmic_flops_per_launch": fl / max(n_big, 1),
+                "all_tcgen05_gemms": {k: {"launches": v[0], "avg_us": 1e3 * v[1] / v[0], "tflops": v[2] / (v[1] * 1e-3) / 1e12}
+                                      for k, v in sorted(by_kind.items(), key=lambda kv: -kv[1][1])[:8]}}
 
     # ---- end to end through the public API with host buffers ------------------------------------------------
     def e2e_step(x_host):
@@ -354,7 +363,8 @@ def run_b200_arm(args):
             "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": world * B, "t_dec": T_DEC,
                        "parallelism": f"utterance-sharded x{world}, adapters replicated, no data-path collective",
                        "l2": "inputs rotate over 3 buffers; each activation tensor (147 MB) exceeds the 126 MB L2",
-                       "weights": "random-init", "rest_of_model": "HF transformers eager (library code)"},
+                       "weights": "random-init",
+                       "rest_of_model": "SDPA = torch/cuDNN, conv front-end / embeddings / lm_head = torch (library code)"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)

@@ -141,6 +141,29 @@ int sar_linear_fwd(const void* x, int x_head_major, const void* W, const void* b
                    void* y, int B, int T, int d_in, int d_out, int act, uint32_t flags, void* stream);
 
 /*
+ * General strided form of sar_linear_fwd (same kernel):  y = act(x·Wᵀ + bias) + residual  with explicit strides, a
+ * ragged K (d_in need not be a multiple of 64: the tail is zero-filled by TMA) and a ragged last N tile.  It exists
+ * for the layers either side of the transformer blocks:
+ *   - lm_head (proj_out, d_out = 51865/51866, no bias): y row stride padded to a multiple of 8 elements
+ *     ($HF/modeling_whisper.py:1135);
+ *   - the convolutional front-end as GEMMs over OVERLAPPING rows of a channels-last, zero-padded frame buffer:
+ *     conv1 (k=3, s=1) = rows of 3*n_mels elements at stride n_mels; conv2 (k=3, s=2) = rows of 3*d at stride 2*d,
+ *     GELU in the epilogue, conv2 also adds the positional embedding as a batch-broadcast residual (:626-633).
+ *   x        bf16, row t of utterance b at x + b*x_batch_stride + t*ldx, d_in elements (rows may overlap)
+ *   W        bf16 [d_out, d_in] contiguous;  bias bf16 [d_out] or NULL
+ *   residual bf16, row at residual + b*res_batch_stride + t*ldr, or NULL; res_broadcast=1: same rows for every b
+ *   y        bf16, row at y + b*y_batch_stride + t*ldy
+ * Strides are in elements; 0 selects the contiguous default (ldx=d_in, x_batch_stride=T*ldx, ...).
+ * When d_out is not a multiple of 8, columns [d_out, round_up(d_out, 8)) of each y row may be overwritten with zeros
+ * (TMA clips stores at 16-byte granularity): give y a row stride of at least round_up(d_out, 8).
+ * Constraints: d_in and every stride multiples of 8; bias / residual need d_out % 64 == 0; 16-byte aligned pointers.
+ */
+int sar_dense_fwd(const void* x, int64_t ldx, int64_t x_batch_stride, const void* W, const void* bias,
+                  const void* residual, int64_t ldr, int64_t res_batch_stride, int res_broadcast, void* y,
+                  int64_t ldy, int64_t y_batch_stride, int B, int T, int d_in, int d_out, int act,
+                  uint32_t flags, void* stream);
+
+/*
  * LayerNorm over the last dimension, fp32 statistics, bf16 in / out (HBM-bound: one read + one write of x):
  *   y[m,:] = (x[m,:] - mean) * rsqrt(var + eps) * gamma + beta
  * Replaces nn.LayerNorm at self_attn_layer_norm / encoder_attn_layer_norm / final_layer_norm / layer_norm

@@ -5,9 +5,18 @@
 // tile, B_k tile) is split in halves between the two CTAs, which halves the per-SM operand ingest from L2 — the
 // limiter of the single-CTA kernel (ncu: tensor pipe 50 % active at 104 B/clk/SM demanded vs ~64 B/clk/SM served).
 //
-// Scheduling: work is the flat list of (unit, N-tile) steps; pair p owns a contiguous, balanced range of it, so
-// the last wave is never more than one tile-step long.  A range that starts in the middle of a unit first runs a
-// U-only pass (loads X and A_k, issues only the N=r MMAs) to rebuild the low-rank intermediate of that unit.
+// Scheduling: work is the flat list of (unit, N-tile) steps.
+//   LORA kernels: pair p owns a contiguous, balanced range of it, so the low-rank intermediate U of a unit is built
+//     once and reused by the following N tiles, and the last wave is never more than one tile-step long.  A range
+//     that starts in the middle of a unit first runs a U-only pass (loads X and A_k, issues only the N=r MMAs).
+//   dense kernels (no low-rank term: out_proj / fc1 / fc2 / base-only projections): steps are dealt round-robin
+//     (pair p takes g = p, p + P, ...), so at any moment the P pairs work on ~P/NT neighbouring units and all N
+//     tiles of each — the X rows of a unit are fetched from HBM once and shared through L2 even when K is large
+//     (fc2: a 256-row X tile is 1.5 MB; with contiguous ranges 74 of them thrash L2 and X is re-read NT times).
+//
+// The kernel is specialised at compile time on <BLOCK_N, LORA, EPI> so that each variant's epilogue is a few hundred
+// instructions: ncu showed the one-size-fits-all epilogue (runtime GELU / residual / scale branches, ~2300
+// instructions per 64-column chunk) stalled on instruction fetch (stall_no_inst) and paced the tensor pipe at 30 %.
 //
 // Roles per CTA (192 threads): warp 0 TMA producer (both CTAs load their halves; completion bytes are signalled on
 // the LEADER's mbarriers), warp 1 TMEM alloc + (leader only) single-thread MMA issue with multicast commits,
@@ -44,35 +53,54 @@ struct K1V2Params {
   const int32_t* utt_adapter;
   const __nv_bfloat16* bias;
   const __nv_bfloat16* residual;   // [B, T, d_out] added in the epilogue (n_seg == 1, row-major y), or null
+  long long ldr, res_bs;           // residual row stride / batch stride in elements (res_bs = 0: broadcast over b)
   int act;                         // SAR_ACT_*: 0 none, 1 erf-GELU applied to (acc + bias) before the residual
   __nv_bfloat16* u_out;
 };
 
-// erf-form GELU (HF ACT2FN["gelu"], what Whisper's fc1 uses): 0.5 v (1 + erf(v / sqrt 2))
-__device__ __forceinline__ float gelu_erf(float v) { return 0.5f * v * (1.0f + erff(v * 0.70710678118654752440f)); }
+enum : int { EPI_RES = 1, EPI_GELU = 2, EPI_SCALE = 4 };
 
-template <int BLOCK_N>
+// erf-form GELU (HF ACT2FN["gelu"], what Whisper's fc1 uses): 0.5 v (1 + erf(v / sqrt 2)).
+// erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far below one bf16 ulp of the output): 5 FMAs + one
+// MUFU.RCP + one MUFU.EX2 per element instead of libdevice erff's two-branch ~25-instruction body.
+__device__ __forceinline__ float gelu_erf(float v) {
+  const float z = fabsf(v) * 0.70710678118654752440f;
+  float t, e;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
+  float q = fmaf(t, 1.061405429f, -1.453152027f);
+  q = fmaf(q, t, 1.421413741f);
+  q = fmaf(q, t, -0.284496736f);
+  q = fmaf(q, t, 0.254829592f);
+  const float erf_abs = fmaf(-q * t, e, 1.0f);
+  const float hv = 0.5f * v;
+  return fmaf(hv, copysignf(erf_abs, v), hv);
+}
+
+template <int BLOCK_N, bool LORA>
 struct V2Smem {
   static constexpr int WH_BYTES = (BLOCK_N / 2) * 128;
-  static constexpr int BPH_BYTES = (BLOCK_N / 2) * 128;
+  static constexpr int BPH_BYTES = LORA ? (BLOCK_N / 2) * 128 : 0;
   static __host__ __device__ int ah_bytes(int r) { return (r / 2) * 128; }                      // bytes TMA writes
   static __host__ __device__ int ah_slot(int r) { return ((r / 2) * 128 + 1023) & ~1023; }      // 1 KB-aligned slot
-  static __host__ __device__ int stage_bytes(int r, int n_sets) { return V2_X_BYTES + WH_BYTES + n_sets * ah_slot(r); }
+  static __host__ __device__ int stage_bytes(int r, int n_sets) {
+    return V2_X_BYTES + WH_BYTES + (LORA ? n_sets * ah_slot(r) : 0);
+  }
   static __host__ __device__ int fixed_bytes(int n_sets) {
-    return n_sets * V2_U_BYTES + BPH_BYTES + 4 * 2 * V2_STG_BYTES + 512;
+    return (LORA ? n_sets * V2_U_BYTES : 0) + BPH_BYTES + 4 * 2 * V2_STG_BYTES + 512;
   }
 };
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool LORA, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V2_THREADS, 1)
 k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
             const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
             const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUtensorMap tm_y1,
             const __grid_constant__ CUtensorMap tm_y2, const K1V2Params p) {
-  using L = V2Smem<BLOCK_N>;
+  using L = V2Smem<BLOCK_N, LORA>;
   constexpr int TMEM_COLS = 512;
   constexpr int U_COL = 2 * BLOCK_N;   // U accumulators: set s at columns [U_COL + 64 s, U_COL + 64 s + r)
-  static_assert(2 * BLOCK_N + 2 * 64 <= TMEM_COLS, "TMEM budget");
+  static_assert(2 * BLOCK_N + (LORA ? 2 * 64 : 0) <= TMEM_COLS, "TMEM budget");
   static_assert(BLOCK_N % 64 == 0 && BLOCK_N <= 256, "BLOCK_N");
 
   extern __shared__ uint8_t smem_raw[];
@@ -81,8 +109,8 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
   const int stage_bytes = L::stage_bytes(p.r, p.n_sets);
   const int ah_slot = L::ah_slot(p.r);
   uint8_t* stages = smem;
-  uint8_t* u_tile = stages + S * stage_bytes;          // [n_sets][16 KB]
-  uint8_t* bp_tile = u_tile + p.n_sets * V2_U_BYTES;
+  uint8_t* u_tile = stages + S * stage_bytes;          // [n_sets][16 KB]   (LORA only)
+  uint8_t* bp_tile = u_tile + (LORA ? p.n_sets * V2_U_BYTES : 0);
   uint8_t* stg = bp_tile + L::BPH_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(stg + 4 * 2 * V2_STG_BYTES);
   uint64_t* full = bars;                          // [S]  leader only (count 1 + tx of BOTH CTAs)
@@ -100,7 +128,7 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1;
-  const bool has_lora = (p.n_adapters > 0) && (p.utt_adapter != nullptr);
+  const bool has_lora = LORA && (p.n_adapters > 0) && (p.utt_adapter != nullptr);
   const uint32_t half = p.swap_halves ? (rank ^ 1u) : rank;   // which half of every B operand this CTA supplies
 
   if (warp == 0 && lane == 0) {
@@ -140,8 +168,10 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
   const int NT = p.n_tiles;
   const int NTS = p.nt_per_seg;
   const int bp_issue_kb = KB > 2 ? KB / 2 : 0;
-  const long long g0 = p.total_steps * pair / p.num_pairs;
-  const long long g1 = p.total_steps * (pair + 1) / p.num_pairs;
+  // LORA: contiguous range [g0, g1);  dense: g = pair, pair + P, ... (see the scheduling note at the top)
+  const long long g0 = LORA ? p.total_steps * pair / p.num_pairs : pair;
+  const long long g1 = LORA ? p.total_steps * (pair + 1) / p.num_pairs : p.total_steps;
+  const long long g_stride = p.num_pairs;
 
   // leader-side barrier addresses as seen from this CTA (shared::cluster window of rank 0)
   auto leader_addr = [&](uint64_t* bar) { return mapa_u32(smem_u32(bar), 0); };
@@ -190,7 +220,7 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
       while (g < g1) {
         const int unit = static_cast<int>(g / NT);
         const int nt_first = static_cast<int>(g - static_cast<long long>(unit) * NT);
-        const int nt_last = static_cast<int>(min(static_cast<long long>(NT), nt_first + (g1 - g)));
+        const int nt_last = LORA ? static_cast<int>(min(static_cast<long long>(NT), nt_first + (g1 - g))) : nt_first + 1;
         const int b = unit / p.tiles_per_utt;
         const int m0 = (unit - b * p.tiles_per_utt) * 256 + rank * V2_ROWS_PER_CTA;
         int k = has_lora ? p.utt_adapter[b] : -1;
@@ -198,7 +228,7 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
         if (k >= 0 && nt_first > 0) k_loop(b, m0, k, -1, true, -1);   // U-only pass
         for (int nt = nt_first; nt < nt_last; ++nt)
           k_loop(b, m0, k, nt, k >= 0 && nt == 0, k >= 0 ? p.seg_set[nt / NTS] : -1);
-        g += nt_last - nt_first;
+        g += LORA ? static_cast<long long>(nt_last - nt_first) : g_stride;
       }
     }
     __syncwarp();
@@ -249,7 +279,7 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
       while (g < g1) {
         const int unit = static_cast<int>(g / NT);
         const int nt_first = static_cast<int>(g - static_cast<long long>(unit) * NT);
-        const int nt_last = static_cast<int>(min(static_cast<long long>(NT), nt_first + (g1 - g)));
+        const int nt_last = LORA ? static_cast<int>(min(static_cast<long long>(NT), nt_first + (g1 - g))) : nt_first + 1;
         const int b = unit / p.tiles_per_utt;
         int k = has_lora ? p.utt_adapter[b] : -1;
         if (k < 0 || k >= p.n_adapters) k = -1;
@@ -277,7 +307,7 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
           }
           umma_commit_2sm(&tmem_full[buf], 0b11);
         }
-        g += nt_last - nt_first;
+        g += LORA ? static_cast<long long>(nt_last - nt_first) : g_stride;
       }
     }
     __syncwarp();
@@ -295,7 +325,7 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
     while (g < g1) {
       const int unit = static_cast<int>(g / NT);
       const int nt_first = static_cast<int>(g - static_cast<long long>(unit) * NT);
-      const int nt_last = static_cast<int>(min(static_cast<long long>(NT), nt_first + (g1 - g)));
+      const int nt_last = LORA ? static_cast<int>(min(static_cast<long long>(NT), nt_first + (g1 - g))) : nt_first + 1;
       const int b = unit / p.tiles_per_utt;
       const int m0 = (unit - b * p.tiles_per_utt) * 256 + rank * V2_ROWS_PER_CTA;
       int k = has_lora ? p.utt_adapter[b] : -1;
@@ -337,27 +367,41 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
         const int n0 = nt * BLOCK_N;                 // column in the concatenated N space (W_cat / bias_cat rows)
         const int seg = nt / NTS;
         const int n0_seg = (nt - seg * NTS) * BLOCK_N;   // column inside this segment's output tensor
-        const float oscale = p.seg_scale[seg];
         const CUtensorMap* ty = seg == 0 ? &tm_y0 : (seg == 1 ? &tm_y1 : &tm_y2);
+        float oscale = 1.0f;
+        if constexpr ((EPI & EPI_SCALE) != 0) oscale = p.seg_scale[seg];
+        const bool rows_live = (m0 + q * 32) < p.T;
+        // residual: this thread's 64 columns of chunk c are one 128-byte line; chunk 0 is requested before the wait on
+        // the accumulator, chunk c+1 while chunk c is converted, so the loads never sit on the critical path
+        uint4 rs[8];
+        const uint4* res_row = nullptr;
+        if constexpr ((EPI & EPI_RES) != 0) {
+          if (m0 + row < p.T) {
+            res_row = reinterpret_cast<const uint4*>(p.residual + static_cast<size_t>(b) * p.res_bs +
+                                                     static_cast<size_t>(m0 + row) * p.ldr + n0_seg);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rs[j] = __ldg(res_row + j);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rs[j] = make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
         mbar_wait(&tmem_full[buf], (tile_iter >> 1) & 1);
         tc_fence_after();
-        const bool rows_live = (m0 + q * 32) < p.T;
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N / 64; ++c) {
           uint32_t v0[32], v1[32];
           const uint32_t taddr = tmem_base + lane_addr + buf * BLOCK_N + c * 64;
           tmem_ld_32x32(taddr, v0);
           tmem_ld_32x32(taddr + 32, v1);
-          uint4 rs[8];
-          if (p.residual != nullptr) {   // this thread's 64 residual columns (one 128-byte line), in flight under the TMEM load
-            if (m0 + row < p.T) {
-              const uint4* rp = reinterpret_cast<const uint4*>(
-                  p.residual + (static_cast<size_t>(b) * p.T + m0 + row) * p.d_out + n0_seg + c * 64);
+          uint4 rn[8];
+          if constexpr ((EPI & EPI_RES) != 0) {
+            if (res_row != nullptr && c + 1 < BLOCK_N / 64) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) rs[j] = __ldg(rp + j);
+              for (int j = 0; j < 8; ++j) rn[j] = __ldg(res_row + (c + 1) * 8 + j);
             } else {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) rs[j] = make_uint4(0u, 0u, 0u, 0u);
+              for (int j = 0; j < 8; ++j) rn[j] = make_uint4(0u, 0u, 0u, 0u);
             }
           }
           if (lane == 0) tma_store_wait_read<1>();
@@ -368,32 +412,27 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
           const uint4* bias4 = p.bias ? reinterpret_cast<const uint4*>(p.bias + n0 + c * 64) : nullptr;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            float bf[8];
+            uint32_t bw[4] = {0u, 0u, 0u, 0u};
             if (bias4) {
               const uint4 bb = __ldg(bias4 + j);
-              const uint32_t w[4] = {bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                bf[2 * i] = __uint_as_float(w[i] << 16);
-                bf[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
-              }
-            } else {
-#pragma unroll
-              for (int i = 0; i < 8; ++i) bf[i] = 0.f;
+              bw[0] = bb.x; bw[1] = bb.y; bw[2] = bb.z; bw[3] = bb.w;
             }
             uint32_t pk[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int e = 8 * j + 2 * i;
-              float a0 = __uint_as_float(e < 32 ? v0[e & 31] : v1[e & 31]) + bf[2 * i];
-              float a1 = __uint_as_float(e < 32 ? v0[(e + 1) & 31] : v1[(e + 1) & 31]) + bf[2 * i + 1];
-              if (p.act == SAR_ACT_GELU) {
+              float a0 = __uint_as_float(e < 32 ? v0[e & 31] : v1[e & 31]) + __uint_as_float(bw[i] << 16);
+              float a1 = __uint_as_float(e < 32 ? v0[(e + 1) & 31] : v1[(e + 1) & 31]) +
+                         __uint_as_float(bw[i] & 0xFFFF0000u);
+              if constexpr ((EPI & EPI_GELU) != 0) {
                 a0 = gelu_erf(a0);
                 a1 = gelu_erf(a1);
               }
-              a0 *= oscale;
-              a1 *= oscale;
-              if (p.residual != nullptr) {
+              if constexpr ((EPI & EPI_SCALE) != 0) {
+                a0 *= oscale;
+                a1 *= oscale;
+              }
+              if constexpr ((EPI & EPI_RES) != 0) {
                 const uint32_t rw = i == 0 ? rs[j].x : (i == 1 ? rs[j].y : (i == 2 ? rs[j].z : rs[j].w));
                 a0 += __uint_as_float(rw << 16);
                 a1 += __uint_as_float(rw & 0xFFFF0000u);
@@ -401,6 +440,10 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
               pk[i] = pack_bf16x2(a0, a1);
             }
             st_shared_v4(srow + ((static_cast<uint32_t>(j) ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
+          }
+          if constexpr ((EPI & EPI_RES) != 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rs[j] = rn[j];
           }
           fence_proxy_async_smem();
           __syncwarp();
@@ -417,7 +460,7 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(tmem_empty_leader[buf]);
       }
-      g += nt_last - nt_first;
+      g += LORA ? static_cast<long long>(nt_last - nt_first) : g_stride;
     }
     if (lane == 0) tma_store_wait_all<0>();
     __syncwarp();
@@ -432,18 +475,18 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
 }
 
 // ------------------------------------------------------------------------------------------------ host
-template <int BLOCK_N>
+template <int BLOCK_N, bool LORA, int EPI>
 static int k1v2_launch(const K1Args& a, cudaStream_t stream) {
-  using L = V2Smem<BLOCK_N>;
+  using L = V2Smem<BLOCK_N, LORA>;
   const DeviceInfo& dev = device_info();
-  const bool has_lora = a.n_adapters > 0 && a.utt_adapter != nullptr && a.A_stack != nullptr && a.Bp_stack != nullptr;
+  const bool has_lora = LORA;
   const int n_seg = a.n_seg > 0 ? a.n_seg : 1;
   const int n_sets = (has_lora && a.n_sets > 0) ? a.n_sets : 1;
 
   K1V2Params p{};
   p.B = a.B; p.T = a.T; p.d_in = a.d_in; p.d_out = a.d_out; p.r = has_lora ? a.r : 16;
   p.tiles_per_utt = (a.T + 255) / 256;
-  p.nt_per_seg = a.d_out / BLOCK_N;
+  p.nt_per_seg = (a.d_out + BLOCK_N - 1) / BLOCK_N;   // ragged last tile: W rows past d_out are zero-filled by TMA
   p.n_seg = n_seg;
   p.n_tiles = n_seg * p.nt_per_seg;
   p.n_sets = n_sets;
@@ -454,7 +497,7 @@ static int k1v2_launch(const K1Args& a, cudaStream_t stream) {
   }
   p.x_head_major = a.x_head_major;
   p.y_head_major = a.y_head_major;
-  p.k_blocks = a.d_in / V2_BLOCK_K;
+  p.k_blocks = (a.d_in + V2_BLOCK_K - 1) / V2_BLOCK_K;   // ragged K: columns past d_in are zero-filled by TMA
   p.n_adapters = has_lora ? a.n_adapters : 0;
   p.total_steps = static_cast<long long>(a.B) * p.tiles_per_utt * p.n_tiles;
   p.scale = a.scale;
@@ -462,9 +505,13 @@ static int k1v2_launch(const K1Args& a, cudaStream_t stream) {
   p.utt_adapter = has_lora ? a.utt_adapter : nullptr;
   p.bias = reinterpret_cast<const __nv_bfloat16*>(a.bias);
   p.residual = reinterpret_cast<const __nv_bfloat16*>(a.residual);
+  p.ldr = a.ldr > 0 ? a.ldr : a.d_out;
+  p.res_bs = a.res_broadcast ? 0 : (a.res_batch_stride > 0 ? a.res_batch_stride : static_cast<long long>(a.T) * p.ldr);
+  const uint64_t ldx = a.ldx > 0 ? a.ldx : a.d_in;
+  const uint64_t x_bs = a.x_batch_stride > 0 ? a.x_batch_stride : static_cast<uint64_t>(a.T) * ldx;
+  const uint64_t ldy = a.ldy > 0 ? a.ldy : a.d_out;
+  const uint64_t y_bs = a.y_batch_stride > 0 ? a.y_batch_stride : static_cast<uint64_t>(a.T) * ldy;
   p.act = a.act;
-  if (p.residual && (n_seg != 1 || a.y_head_major))
-    return fail(SAR_EINVAL, "k1v2: residual needs one row-major output segment");
   p.u_out = (has_lora && n_sets == 1) ? reinterpret_cast<__nv_bfloat16*>(a.u_out) : nullptr;
 
   const int stage_bytes = L::stage_bytes(p.r, n_sets);
@@ -493,7 +540,7 @@ static int k1v2_launch(const K1Args& a, cudaStream_t stream) {
     if ((rc = make_tmap_bf16(&tm_x, a.x, 4, dims, strides, box))) return rc;
   } else {
     const uint64_t dims[3] = {(uint64_t)a.d_in, (uint64_t)a.T, (uint64_t)a.B};
-    const uint64_t strides[2] = {(uint64_t)a.d_in * 2, (uint64_t)a.T * a.d_in * 2};
+    const uint64_t strides[2] = {ldx * 2, x_bs * 2};   // rows may overlap (ldx < d_in): conv-as-GEMM windows
     const uint32_t box[3] = {V2_BLOCK_K, V2_ROWS_PER_CTA, 1};
     if ((rc = make_tmap_bf16(&tm_x, a.x, 3, dims, strides, box))) return rc;
   }
@@ -508,7 +555,7 @@ static int k1v2_launch(const K1Args& a, cudaStream_t stream) {
       if ((rc = make_tmap_bf16(&tm_y[s], yp, 4, dims, strides, box))) return rc;
     } else {
       const uint64_t dims[3] = {(uint64_t)a.d_out, (uint64_t)a.T, (uint64_t)a.B};
-      const uint64_t strides[2] = {(uint64_t)a.d_out * 2, (uint64_t)a.T * a.d_out * 2};
+      const uint64_t strides[2] = {ldy * 2, y_bs * 2};
       const uint32_t box[3] = {64, 32, 1};
       if ((rc = make_tmap_bf16(&tm_y[s], yp, 3, dims, strides, box))) return rc;
     }
@@ -534,7 +581,7 @@ static int k1v2_launch(const K1Args& a, cudaStream_t stream) {
     }
   }
 
-  auto kern = k1v2_kernel<BLOCK_N>;
+  auto kern = k1v2_kernel<BLOCK_N, LORA, EPI>;
   static thread_local int smem_set = 0;
   if (smem_set < smem_bytes) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.max_smem_optin);
@@ -547,10 +594,47 @@ static int k1v2_launch(const K1Args& a, cudaStream_t stream) {
   return SAR_OK;
 }
 
+template <int BLOCK_N, bool LORA>
+static int k1v2_dispatch_epi(const K1Args& a, int epi, cudaStream_t stream) {
+  switch (epi) {
+    case 0: return k1v2_launch<BLOCK_N, LORA, 0>(a, stream);
+    case EPI_SCALE: return k1v2_launch<BLOCK_N, LORA, EPI_SCALE>(a, stream);
+    case EPI_RES:
+      if constexpr (!LORA) return k1v2_launch<BLOCK_N, false, EPI_RES>(a, stream);
+      break;
+    case EPI_GELU:
+      if constexpr (!LORA) return k1v2_launch<BLOCK_N, false, EPI_GELU>(a, stream);
+      break;
+    case EPI_GELU | EPI_RES:
+      if constexpr (!LORA) return k1v2_launch<BLOCK_N, false, EPI_GELU | EPI_RES>(a, stream);
+      break;
+    default: break;
+  }
+  return fail(SAR_EINVAL, "k1v2: unsupported epilogue combination (residual / GELU are dense-only)");
+}
+
 int k1v2_qv_lora_fwd(const K1Args& a, int block_n, cudaStream_t stream) {
+  const bool lora = a.n_adapters > 0 && a.utt_adapter != nullptr && a.A_stack != nullptr && a.Bp_stack != nullptr;
+  const int n_seg = a.n_seg > 0 ? a.n_seg : 1;
+  int epi = 0;
+  if (a.residual) epi |= EPI_RES;
+  if (a.act == SAR_ACT_GELU) epi |= EPI_GELU;
+  if (a.n_seg > 0)
+    for (int s = 0; s < n_seg; ++s)
+      if (a.seg_scale[s] != 1.0f) epi |= EPI_SCALE;
+  if (a.residual && (n_seg != 1 || a.y_head_major))
+    return fail(SAR_EINVAL, "k1v2: residual needs one row-major output segment");
+  if (lora) {
+    switch (block_n) {
+      case 128: return k1v2_dispatch_epi<128, true>(a, epi, stream);
+      case 192: return k1v2_dispatch_epi<192, true>(a, epi, stream);
+      default: return fail(SAR_EINVAL, "k1v2: unsupported BLOCK_N for the LoRA kernel (128 or 192)");
+    }
+  }
   switch (block_n) {
-    case 128: return k1v2_launch<128>(a, stream);
-    case 192: return k1v2_launch<192>(a, stream);
+    case 128: return k1v2_dispatch_epi<128, false>(a, epi, stream);
+    case 192: return k1v2_dispatch_epi<192, false>(a, epi, stream);
+    case 256: return k1v2_dispatch_epi<256, false>(a, epi, stream);
     default: return fail(SAR_EINVAL, "k1v2: unsupported BLOCK_N");
   }
 }
@@ -560,8 +644,24 @@ int attn_proj_fwd(const K1Args& a, cudaStream_t stream) {
   if (!a.x || !a.W) return fail(SAR_EINVAL, "attn_proj: null x/W");
   if (a.B <= 0 || a.T <= 0) return fail(SAR_EINVAL, "attn_proj: B and T must be positive");
   if (a.n_seg < 1 || a.n_seg > 3) return fail(SAR_EINVAL, "attn_proj: n_seg must be 1, 2 or 3");
-  if (a.d_in % 64 || a.d_out % 128 || a.d_in <= 0 || a.d_out <= 0)
-    return fail(SAR_EINVAL, "attn_proj: d_in must be a multiple of 64 and d_out of 128");
+  if (a.d_in <= 0 || a.d_out <= 0) return fail(SAR_EINVAL, "attn_proj: d_in and d_out must be positive");
+  const bool plain = a.n_seg == 1 && !a.x_head_major && !a.y_head_major &&
+                     !(a.n_adapters > 0 && a.utt_adapter && a.A_stack && a.Bp_stack);
+  if (plain) {
+    // single dense segment: ragged K (zero-filled by TMA) and a ragged last N tile are allowed
+    const long long ldx = a.ldx > 0 ? a.ldx : a.d_in, ldy = a.ldy > 0 ? a.ldy : a.d_out;
+    if (a.d_in % 8 || ldx % 8 || ldy % 8 || (a.x_batch_stride % 8) || (a.y_batch_stride % 8))
+      return fail(SAR_EINVAL, "dense: d_in and every stride must be a multiple of 8 elements (16 bytes)");
+    if (a.d_out % 64 && (a.bias || a.residual))
+      return fail(SAR_EINVAL, "dense: bias / residual need d_out to be a multiple of 64");
+    if (a.residual && ((a.ldr > 0 ? a.ldr : a.d_out) % 8 || (a.res_batch_stride > 0 && a.res_batch_stride % 8)))
+      return fail(SAR_EINVAL, "dense: residual strides must be multiples of 8 elements");
+  } else {
+    if (a.d_in % 64 || a.d_out % 128)
+      return fail(SAR_EINVAL, "attn_proj: d_in must be a multiple of 64 and d_out of 128");
+    if (a.ldx || a.ldy || a.x_batch_stride || a.y_batch_stride)
+      return fail(SAR_EINVAL, "attn_proj: custom strides are supported for single dense row-major segments only");
+  }
   const bool lora = a.n_adapters > 0 && a.utt_adapter && a.A_stack && a.Bp_stack;
   if (lora && (a.r % 16 || a.r < 16 || a.r > 64)) return fail(SAR_EINVAL, "attn_proj: r must be 16, 32, 48 or 64");
   if (lora && (a.n_sets < 1 || a.n_sets > 2)) return fail(SAR_EINVAL, "attn_proj: n_sets must be 1 or 2");
@@ -570,8 +670,9 @@ int attn_proj_fwd(const K1Args& a, cudaStream_t stream) {
                  reinterpret_cast<uintptr_t>(a.bias);
   for (int s = 0; s < a.n_seg; ++s) al |= reinterpret_cast<uintptr_t>(a.y_seg[s]);
   if (al & 15) return fail(SAR_EINVAL, "attn_proj: pointers must be 16-byte aligned");
-  int bn = a.block_n_override ? a.block_n_override : ((a.d_out % 192 == 0) ? 192 : 128);
-  if (a.d_out % bn) return fail(SAR_EINVAL, "attn_proj: d_out not divisible by BLOCK_N");
+  int bn = a.block_n_override;
+  if (!bn) bn = (!lora && (a.d_out % 256 == 0 || (plain && a.d_out > 2048))) ? 256 : ((a.d_out % 192 == 0) ? 192 : 128);
+  if (a.d_out % bn && !plain) return fail(SAR_EINVAL, "attn_proj: d_out not divisible by BLOCK_N");
   return k1v2_qv_lora_fwd(a, bn, stream);
 }
 

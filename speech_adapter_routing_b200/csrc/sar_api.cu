@@ -182,6 +182,30 @@ int sar_linear_fwd(const void* x, int x_head_major, const void* W, const void* b
   return attn_proj_fwd(a, static_cast<cudaStream_t>(stream));
 }
 
+int sar_dense_fwd(const void* x, int64_t ldx, int64_t x_batch_stride, const void* W, const void* bias,
+                  const void* residual, int64_t ldr, int64_t res_batch_stride, int res_broadcast, void* y,
+                  int64_t ldy, int64_t y_batch_stride, int B, int T, int d_in, int d_out, int act, uint32_t flags,
+                  void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  if (act != SAR_ACT_NONE && act != SAR_ACT_GELU) return fail(SAR_EINVAL, "sar_dense_fwd: unknown activation");
+  if (ldx < 0 || x_batch_stride < 0 || ldy < 0 || y_batch_stride < 0 || ldr < 0 || res_batch_stride < 0)
+    return fail(SAR_EINVAL, "sar_dense_fwd: negative stride");
+  if (reinterpret_cast<uintptr_t>(residual) & 15) return fail(SAR_EINVAL, "sar_dense_fwd: residual must be 16-byte aligned");
+  K1Args a{};
+  a.x = x; a.W = W; a.bias = bias; a.B = B; a.T = T; a.d_in = d_in; a.d_out = d_out; a.r = 16; a.scale = 0.f;
+  a.block_n_override = static_cast<int>((flags >> 8) & 0x3FF);
+  a.grid_override = static_cast<int>((flags >> 18) & 0x3FF);
+  a.n_seg = 1; a.n_sets = 1;
+  a.seg_set[0] = a.seg_set[1] = a.seg_set[2] = -1;
+  a.seg_scale[0] = a.seg_scale[1] = a.seg_scale[2] = 1.0f;
+  a.y_seg[0] = y;
+  a.residual = residual; a.act = act;
+  a.ldx = ldx; a.x_batch_stride = x_batch_stride; a.ldy = ldy; a.y_batch_stride = y_batch_stride;
+  a.ldr = ldr; a.res_batch_stride = res_batch_stride; a.res_broadcast = res_broadcast;
+  return attn_proj_fwd(a, static_cast<cudaStream_t>(stream));
+}
+
 int sar_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, int64_t M, int d, float eps,
                       void* stream) {
   int rc = require_sm100();

@@ -58,6 +58,11 @@ struct K1Args {
   int y_head_major;      // every y is [B, d_out/64, T, 64]
   const void* residual;  // bf16 [B, T, d_out] added in the epilogue (single row-major segment only)
   int act;               // SAR_ACT_*
+  // ---- strided dense-layer extensions (single row-major segment, no LoRA); 0 = contiguous default
+  long long ldx, x_batch_stride;     // x row / batch stride in elements (rows may overlap: conv-as-GEMM windows)
+  long long ldy, y_batch_stride;     // y row / batch stride in elements
+  long long ldr, res_batch_stride;   // residual row stride (0 = d_out) / batch stride (0 = T*ldr)
+  int res_broadcast;                 // 1: the same [T, d_out] residual for every b (positional embedding)
 };
 int k1_qv_lora_fwd(const K1Args& a, cudaStream_t stream);
 int k1v2_qv_lora_fwd(const K1Args& a, int block_n, cudaStream_t stream);

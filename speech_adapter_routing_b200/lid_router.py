@@ -24,7 +24,7 @@ import torch.nn.functional as F
 from . import ops
 from .lora_linear import RoutedLoRALinear
 from .peft_compat import LoraConfig, PeftModel, inject_lora, lora_modules
-from .routing import base_only, route
+from .routing import base_only, route, route_base
 
 logger = logging.getLogger(__name__)
 
@@ -245,8 +245,9 @@ class EncoderFeatureExtractor(nn.Module):
     @torch.no_grad()
     def forward(self, input_features: torch.Tensor, output_hidden_states: bool = True) -> torch.Tensor:
         enc = self._get_encoder()
-        want_all = output_hidden_states or (self.layer_index != -1)
-        with route(base_only(input_features.shape[0], input_features.device)):
+        # the reference always asks for every layer's states (:463) but only reads them when layer_index != -1
+        want_all = self.layer_index != -1
+        with route_base():
             out = enc(input_features, output_hidden_states=want_all, return_dict=True)
         if self.layer_index == -1:
             return out.last_hidden_state

@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .routing import current_utt_adapter
+from .routing import current_utt_adapter, routing_base_only
 
 
 class _QVLoRAFn(torch.autograd.Function):
@@ -167,6 +167,8 @@ class RoutedLoRALinear(nn.Module):
     def resolve_index(self, B: int, device) -> Optional[torch.Tensor]:
         """int32 [B] adapter index per utterance for this call: the routing context if one is active, else the
         module's active adapter for every utterance; None = base weights only."""
+        if routing_base_only():
+            return None
         idx = current_utt_adapter()
         if idx is None:
             return self._default_index(B, device)

@@ -204,6 +204,29 @@ def linear_fwd(x: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], r
     return y
 
 
+def dense_fwd(x_base: torch.Tensor, ldx: int, x_batch_stride: int, W: torch.Tensor, bias: Optional[torch.Tensor],
+              y_base: torch.Tensor, ldy: int, y_batch_stride: int, B: int, T: int, d_in: int, d_out: int,
+              act: int = _lib.SAR_ACT_NONE, residual: Optional[torch.Tensor] = None, ldr: int = 0,
+              res_batch_stride: int = 0, res_broadcast: bool = False, block_n: int = 0, grid: int = 0) -> None:
+    """General strided dense layer (sar_dense_fwd): y[b,t,:] = act(x[b,t,:]·Wᵀ + bias) + residual[b,t,:] where row
+    (b, t) of x starts at ``x_base.data_ptr() + 2*(b*x_batch_stride + t*ldx)`` (rows may overlap) and likewise for y /
+    residual.  ``x_base`` / ``y_base`` are tensors whose first element is the origin; the caller owns bounds."""
+    _need_cuda(x_base, W, bias, y_base, residual)
+    for t, name in ((x_base, "x"), (W, "W"), (bias, "bias"), (y_base, "y"), (residual, "residual")):
+        if t is not None and t.dtype != torch.bfloat16:
+            raise TypeError(f"{name} must be torch.bfloat16")
+    if not W.is_contiguous() or tuple(W.shape) != (d_out, d_in):
+        raise ValueError("W must be contiguous [d_out, d_in]")
+    flags = ((block_n & 0x3FF) << 8) | ((grid & 0x3FF) << 18)
+
+    def launch():
+        check(lib().sar_dense_fwd(_ptr(x_base), int(ldx), int(x_batch_stride), _ptr(W), _ptr(bias), _ptr(residual),
+                                  int(ldr), int(res_batch_stride), int(res_broadcast), _ptr(y_base), int(ldy),
+                                  int(y_batch_stride), B, T, d_in, d_out, int(act), flags, _stream(x_base)))
+    _time_k1(K1_TIMELINE, "dense", B * T, d_in, d_out, 2.0 * B * T * d_in * d_out, launch)
+    LAUNCHES["linear"] += 1
+
+
 def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """LayerNorm over the last dim (sar_layernorm_fwd): bf16 in/out, fp32 statistics."""

@@ -19,6 +19,7 @@ class _RoutingState(threading.local):
     def __init__(self) -> None:
         self.utt_adapter: Optional[torch.Tensor] = None
         self.active = False
+        self.base_only = False
 
 
 _state = _RoutingState()
@@ -33,6 +34,22 @@ def routing_active() -> bool:
     return _state.active
 
 
+def routing_base_only() -> bool:
+    """True inside ``route_base()``: every LoRA'd projection runs on its base weights (dense kernel, no adapter
+    operands streamed) — the LID feature pass of the reference runs on the un-adapted encoder (adapter_router.py:441-474)."""
+    return _state.base_only
+
+
+@contextmanager
+def route_base():
+    prev = (_state.utt_adapter, _state.active, _state.base_only)
+    _state.utt_adapter, _state.active, _state.base_only = None, False, True
+    try:
+        yield
+    finally:
+        _state.utt_adapter, _state.active, _state.base_only = prev
+
+
 @contextmanager
 def route(utt_adapter: Optional[torch.Tensor]):
     """Run the enclosed forward with per-utterance adapter indices.  ``None`` restores module defaults
@@ -41,12 +58,12 @@ def route(utt_adapter: Optional[torch.Tensor]):
         if utt_adapter.dtype != torch.int32:
             utt_adapter = utt_adapter.to(torch.int32)
         utt_adapter = utt_adapter.contiguous()
-    prev = (_state.utt_adapter, _state.active)
-    _state.utt_adapter, _state.active = utt_adapter, utt_adapter is not None
+    prev = (_state.utt_adapter, _state.active, _state.base_only)
+    _state.utt_adapter, _state.active, _state.base_only = utt_adapter, utt_adapter is not None, False
     try:
         yield
     finally:
-        _state.utt_adapter, _state.active = prev
+        _state.utt_adapter, _state.active, _state.base_only = prev
 
 
 def base_only(batch_size: int, device) -> torch.Tensor:

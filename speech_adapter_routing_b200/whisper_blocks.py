@@ -20,6 +20,7 @@ still RoutedLoRALinear (libsar K1/K3), so neither branch is a CPU or eager-LoRA 
 """
 from __future__ import annotations
 
+import math
 import types
 from typing import Dict, List, Optional, Tuple
 
@@ -62,23 +63,29 @@ class _ProjPack:
         if key == self.key:
             return self
         self.key = key
+        # an output scale that is a power of two (Whisper: head_dim^-0.5 = 2^-3 on q) is folded into the bf16
+        # operands — exact, since it only shifts exponents — so the kernel's plain epilogue variant is used
+        fold = [s != 1.0 and math.frexp(s)[0] == 0.5 for s in self.seg_scale]
+        self.kernel_scale = [1.0 if f else s for s, f in zip(self.seg_scale, fold)]
         Ws, bs = [], []
-        for m in self.mods:
+        for m, s, f in zip(self.mods, self.seg_scale, fold):
             W, b = _lin_params(m)
-            Ws.append(W.detach().to(torch.bfloat16))
-            bs.append(torch.zeros(W.shape[0], dtype=torch.bfloat16, device=W.device) if b is None
-                      else b.detach().to(torch.bfloat16))
+            W = W.detach().to(torch.bfloat16)
+            b = (torch.zeros(W.shape[0], dtype=torch.bfloat16, device=W.device) if b is None
+                 else b.detach().to(torch.bfloat16))
+            Ws.append(W * s if f else W)
+            bs.append(b * s if f else b)
         self.W = torch.cat(Ws, 0).contiguous()
         self.bias = torch.cat(bs, 0).contiguous()
         self.seg_set: List[int] = []
         As, Bps, scales = [], [], []
         self.lora_mods: List[RoutedLoRALinear] = []
-        for m in self.mods:
+        for m, s, f in zip(self.mods, self.seg_scale, fold):
             if isinstance(m, RoutedLoRALinear) and m.adapter_order:
                 st = m._stacks()
                 self.seg_set.append(len(As))
                 As.append(st["A"])
-                Bps.append(st["Bp"])
+                Bps.append(st["Bp"] * s if f else st["Bp"])
                 scales.append(st["scale"])
                 self.lora_mods.append(m)
             else:
@@ -106,7 +113,7 @@ class _ProjPack:
         lora = idx is not None and self.A is not None
         return ops.attn_proj_fwd(x, self.W, self.bias, self.A if lora else None, self.Bp if lora else None,
                                  idx if lora else None, self.seg_set if lora else [-1] * len(self.seg_set),
-                                 self.seg_scale, self.n_sets if lora else 1, self.scale, y_head_major=True)
+                                 self.kernel_scale, self.n_sets if lora else 1, self.scale, y_head_major=True)
 
 
 class _DensePack:
@@ -239,6 +246,147 @@ def _decoder_layer_forward(self, hidden_states: torch.Tensor, attention_mask: Op
     return _dense(f, pk["fc2"], residual=h, inplace=True)
 
 
+# ------------------------------------------------------------------------------------------------ model-level bodies
+class _ConvPack:
+    """Whisper's conv1 / conv2 as GEMM operands: weight [d_out, C, 3] -> [d_out, 3*C] with the tap index major, matching
+    one im2col row = (frame t-1 | frame t | frame t+1) of a channels-last frame buffer."""
+
+    def __init__(self, conv: nn.Conv1d):
+        self.m = conv
+        self.key = None
+
+    @torch.no_grad()
+    def get(self):
+        key = _pver(self.m.weight, self.m.bias)
+        if key != self.key:
+            self.key = key
+            w = self.m.weight.detach().to(torch.bfloat16)
+            self.W = w.permute(0, 2, 1).reshape(w.shape[0], -1).contiguous()
+            self.b = self.m.bias.detach().to(torch.bfloat16).contiguous()
+        return self
+
+
+def _conv_frontend_supported(enc: nn.Module) -> bool:
+    c1, c2 = enc.conv1, enc.conv2
+    ok = lambda c, s: (isinstance(c, nn.Conv1d) and c.kernel_size == (3,) and c.stride == (s,) and c.padding == (1,)
+                       and c.dilation == (1,) and c.groups == 1 and c.bias is not None)
+    return ok(c1, 1) and ok(c2, 2) and c1.in_channels % 8 == 0 and c1.out_channels % 128 == 0
+
+
+def _conv_frontend(enc: nn.Module, x: torch.Tensor) -> torch.Tensor:
+    """gelu(conv1) -> gelu(conv2) -> + positions, as two launches of the tcgen05 pair kernel over OVERLAPPING rows of
+    channels-last, zero-padded frame buffers (conv-as-GEMM without materialising im2col), replacing cuDNN's
+    NCHW<->NHWC transposes + implicit GEMM + separate bias / GELU / permute / add kernels
+    ($HF/models/whisper/modeling_whisper.py:626-633)."""
+    pk = enc._sar_pack
+    B, C, L = x.shape
+    d = enc.conv1.out_channels
+    T2 = (L - 1) // 2 + 1
+    key = (B, C, L, x.device)
+    ws = pk.get("conv_ws")
+    if ws is None or ws[0] != key:
+        buf1 = torch.zeros(B, L + 2, C, dtype=torch.bfloat16, device=x.device)
+        buf2 = torch.zeros(B, L + 2, d, dtype=torch.bfloat16, device=x.device)   # pad frames 0 and L+1 stay zero
+        ws = (key, buf1, buf2)
+        pk["conv_ws"] = ws
+    _, buf1, buf2 = ws
+    buf1[:, 1:L + 1, :].copy_(x.transpose(1, 2))
+    c1, c2 = pk["conv1"].get(), pk["conv2"].get()
+    # conv1 (k=3, s=1, p=1): row t = buffer frames t, t+1, t+2 -> 3C elements at stride C; output into buf2 frame t+1
+    ops.dense_fwd(buf1, C, (L + 2) * C, c1.W, c1.b, buf2[:, 1:], d, (L + 2) * d, B, L, 3 * C, d, act=SAR_ACT_GELU)
+    # conv2 (k=3, s=2, p=1): row t = buffer frames 2t, 2t+1, 2t+2 -> 3d elements at stride 2d; + positions (broadcast)
+    pos = pk["pos"].get().W
+    h = torch.empty(B, T2, d, dtype=torch.bfloat16, device=x.device)
+    ops.dense_fwd(buf2, 2 * d, (L + 2) * d, c2.W, c2.b, h, d, T2 * d, B, T2, 3 * d, d, act=SAR_ACT_GELU,
+                  residual=pos, ldr=d, res_broadcast=True)
+    return h
+
+
+class _EmbedPack:
+    def __init__(self, m: nn.Embedding):
+        self.m = m
+        self.key = None
+
+    @torch.no_grad()
+    def get(self):
+        key = _pver(self.m.weight)
+        if key != self.key:
+            self.key = key
+            self.W = self.m.weight.detach().to(torch.bfloat16).contiguous()
+        return self
+
+
+def _encoder_forward(self, input_features, attention_mask=None, **kwargs):
+    """WhisperEncoder.forward ($HF/models/whisper/modeling_whisper.py:590-647) without HF's per-call bookkeeping."""
+    x = input_features
+    fast = (FUSED_BLOCKS_ENABLED and isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.bfloat16
+            and x.dim() == 3 and not torch.is_grad_enabled() and not self.training
+            and not kwargs.get("output_attentions") and not kwargs.get("output_hidden_states")
+            and kwargs.get("return_dict", True) is not False)
+    if not fast:
+        return self._sar_hf_forward(input_features, attention_mask=attention_mask, **kwargs)
+    from transformers.modeling_outputs import BaseModelOutput
+
+    expected = self.config.max_source_positions * self.conv1.stride[0] * self.conv2.stride[0]
+    if x.shape[-1] != expected:
+        raise ValueError(f"Whisper expects the mel input features to be of length {expected}, but found {x.shape[-1]}. "
+                         f"Make sure to pad the input mel features to {expected}.")
+    pk = self._sar_pack
+    if pk["conv_ok"]:
+        h = _conv_frontend(self, x.contiguous())
+    else:
+        h = F.gelu(self.conv2(F.gelu(self.conv1(x)))).permute(0, 2, 1) + self.embed_positions.weight
+    for layer in self.layers:
+        h = layer(h, None)
+    ln = pk["ln"].get()
+    h = ops.layernorm_fwd(h.contiguous(), ln.W, ln.b, self.layer_norm.eps)
+    return BaseModelOutput(last_hidden_state=h)
+
+
+def _decoder_forward(self, input_ids=None, attention_mask=None, encoder_hidden_states=None, past_key_values=None,
+                     inputs_embeds=None, position_ids=None, use_cache=None, **kwargs):
+    """WhisperDecoder.forward (:737-805) for the teacher-forced, cache-free case: no mask construction (HF's
+    create_causal_mask costs ~15 tiny launches and one host sync per call), SDPA's causal flag instead."""
+    if use_cache is None:
+        use_cache = bool(getattr(self.config, "use_cache", False))
+    fast = (FUSED_BLOCKS_ENABLED and input_ids is not None and inputs_embeds is None and attention_mask is None
+            and past_key_values is None and not use_cache and position_ids is None and input_ids.is_cuda
+            and not torch.is_grad_enabled() and not self.training and self.embed_tokens.weight.dtype == torch.bfloat16
+            and (encoder_hidden_states is None or encoder_hidden_states.dtype == torch.bfloat16)
+            and not kwargs.get("output_attentions") and not kwargs.get("output_hidden_states")
+            and kwargs.get("return_dict", True) is not False)
+    if not fast:
+        return self._sar_hf_forward(input_ids=input_ids, attention_mask=attention_mask,
+                                    encoder_hidden_states=encoder_hidden_states, past_key_values=past_key_values,
+                                    inputs_embeds=inputs_embeds, position_ids=position_ids, use_cache=use_cache, **kwargs)
+    from transformers.modeling_outputs import BaseModelOutputWithPastAndCrossAttentions
+
+    T = input_ids.shape[-1]
+    h = self.embed_tokens(input_ids.view(-1, T)) + self.embed_positions.weight[:T]
+    for layer in self.layers:
+        h = layer(h, None, encoder_hidden_states, encoder_attention_mask=None, past_key_values=None, use_cache=False)
+    ln = self._sar_pack["ln"].get()
+    h = ops.layernorm_fwd(h.contiguous(), ln.W, ln.b, self.layer_norm.eps)
+    return BaseModelOutputWithPastAndCrossAttentions(last_hidden_state=h, past_key_values=None)
+
+
+def _lm_head_forward(self, x: torch.Tensor) -> torch.Tensor:
+    """proj_out (:1135): [.., d] x [V, d]ᵀ on the pair kernel.  V = 51865 / 51866 is not a multiple of 8, so the logits
+    live in a buffer whose row stride is padded to 8 elements and the returned tensor is the [.., :V] view of it."""
+    W = self.weight
+    if not (FUSED_BLOCKS_ENABLED and x.is_cuda and x.dtype == torch.bfloat16 and W.dtype == torch.bfloat16
+            and self.bias is None and not torch.is_grad_enabled() and W.is_contiguous() and x.shape[-1] % 8 == 0):
+        return self._sar_hf_forward(x)
+    d = x.shape[-1]
+    M = x.numel() // d
+    V = W.shape[0]
+    ldy = (V + 7) // 8 * 8
+    x2 = x.contiguous().view(M, d)
+    buf = torch.empty(M, ldy, dtype=torch.bfloat16, device=x.device)
+    ops.dense_fwd(x2, d, 0, W.detach(), None, buf, ldy, 0, 1, M, d, V)
+    return buf.view(*x.shape[:-1], ldy)[..., :V]
+
+
 # ------------------------------------------------------------------------------------------------ installation
 def _layer_supported(layer: nn.Module, decoder: bool) -> bool:
     if not _is_gelu(layer) or not _supported_attn(layer.self_attn):
@@ -251,40 +399,61 @@ def _layer_supported(layer: nn.Module, decoder: bool) -> bool:
     return all(isinstance(m, nn.LayerNorm) and m.elementwise_affine and m.bias is not None for m in lns)
 
 
+def _bind(module: nn.Module, fn, pack: Dict[str, object]) -> None:
+    if not hasattr(module, "_sar_hf_forward"):
+        object.__setattr__(module, "_sar_hf_forward", module.forward)   # the bound class method (HF's body)
+    object.__setattr__(module, "_sar_pack", pack)
+    object.__setattr__(module, "forward", types.MethodType(fn, module))
+
+
 def install_fused_blocks(model: nn.Module) -> int:
-    """Re-bind ``forward`` of every supported WhisperEncoderLayer / WhisperDecoderLayer under ``model`` (idempotent).
-    Call again after module surgery (e.g. after LoRA injection replaced q_proj / v_proj).  Returns #layers bound."""
-    from transformers.models.whisper.modeling_whisper import WhisperDecoderLayer, WhisperEncoderLayer
+    """Re-bind ``forward`` of every supported WhisperEncoderLayer / WhisperDecoderLayer under ``model``, of the
+    WhisperEncoder / WhisperDecoder that own them and of the lm head (idempotent).  Call again after module surgery
+    (e.g. after LoRA injection replaced q_proj / v_proj).  Returns the number of modules bound."""
+    from transformers.models.whisper.modeling_whisper import (WhisperDecoder, WhisperDecoderLayer, WhisperEncoder,
+                                                              WhisperEncoderLayer, WhisperForConditionalGeneration)
 
     n = 0
-    for layer in model.modules():
-        dec = isinstance(layer, WhisperDecoderLayer)
-        if not dec and not isinstance(layer, WhisperEncoderLayer):
-            continue
-        if not _layer_supported(layer, dec):
-            continue
-        if not hasattr(layer, "_sar_hf_forward"):
-            object.__setattr__(layer, "_sar_hf_forward", layer.forward)   # the bound class method (HF's body)
-        pack: Dict[str, object] = {
-            "self": _AttnPack(layer.self_attn, cross=False),
-            "ln1": _DensePack(layer.self_attn_layer_norm),
-            "ln3": _DensePack(layer.final_layer_norm),
-            "fc1": _DensePack(layer.fc1),
-            "fc2": _DensePack(layer.fc2),
-        }
-        if dec:
-            pack["cross"] = _AttnPack(layer.encoder_attn, cross=True)
-            pack["ln2"] = _DensePack(layer.encoder_attn_layer_norm)
-        object.__setattr__(layer, "_sar_pack", pack)
-        object.__setattr__(layer, "forward",
-                           types.MethodType(_decoder_layer_forward if dec else _encoder_layer_forward, layer))
-        n += 1
+    for module in list(model.modules()):
+        if isinstance(module, (WhisperDecoderLayer, WhisperEncoderLayer)):
+            dec = isinstance(module, WhisperDecoderLayer)
+            if not _layer_supported(module, dec):
+                continue
+            pack: Dict[str, object] = {
+                "self": _AttnPack(module.self_attn, cross=False),
+                "ln1": _DensePack(module.self_attn_layer_norm),
+                "ln3": _DensePack(module.final_layer_norm),
+                "fc1": _DensePack(module.fc1),
+                "fc2": _DensePack(module.fc2),
+            }
+            if dec:
+                pack["cross"] = _AttnPack(module.encoder_attn, cross=True)
+                pack["ln2"] = _DensePack(module.encoder_attn_layer_norm)
+            _bind(module, _decoder_layer_forward if dec else _encoder_layer_forward, pack)
+            n += 1
+        elif isinstance(module, WhisperEncoder):
+            if not (isinstance(module.layer_norm, nn.LayerNorm) and module.layer_norm.bias is not None):
+                continue
+            _bind(module, _encoder_forward, {"ln": _DensePack(module.layer_norm), "conv1": _ConvPack(module.conv1),
+                                             "conv2": _ConvPack(module.conv2), "pos": _EmbedPack(module.embed_positions),
+                                             "conv_ok": _conv_frontend_supported(module)})
+            n += 1
+        elif isinstance(module, WhisperDecoder):
+            if not (isinstance(module.layer_norm, nn.LayerNorm) and module.layer_norm.bias is not None):
+                continue
+            _bind(module, _decoder_forward, {"ln": _DensePack(module.layer_norm)})
+            n += 1
+        elif isinstance(module, WhisperForConditionalGeneration):
+            head = module.proj_out
+            if isinstance(head, nn.Linear) and head.bias is None:
+                _bind(head, _lm_head_forward, {})
+                n += 1
     return n
 
 
 def uninstall_fused_blocks(model: nn.Module) -> None:
-    for layer in model.modules():
-        if hasattr(layer, "_sar_hf_forward"):
-            object.__delattr__(layer, "forward")
-            object.__delattr__(layer, "_sar_hf_forward")
-            object.__delattr__(layer, "_sar_pack")
+    for module in model.modules():
+        if hasattr(module, "_sar_hf_forward"):
+            object.__delattr__(module, "forward")
+            object.__delattr__(module, "_sar_hf_forward")
+            object.__delattr__(module, "_sar_pack")

@@ -282,6 +282,12 @@ def test_save_and_reload_adapter_on_gpu(cuda_dev, tmp_path, monkeypatch):
     w2.eval()
     with torch.no_grad():
         b = w2(input_features=x, decoder_input_ids=dec.to("cuda")).logits
-    assert torch.equal(a, b)
+    # w was built for training (use_cache off -> fused decoder blocks); the reloaded model keeps HF's use_cache
+    # default (KV cache -> HF decoder bodies over the K1 module slots): same weights, different rounding points
+    assert (a.float() - b.float()).abs().max().item() <= 2e-2 * a.float().abs().max().item()
+    w2.model.config.use_cache = w.model.config.use_cache
+    with torch.no_grad():
+        b = w2(input_features=x, decoder_input_ids=dec.to("cuda")).logits
+    assert torch.equal(a, b)   # same code path -> bit-identical after the save / load round trip
     ids = w2.generate(x, max_new_tokens=4)
     assert ids.shape[0] == 2

@@ -312,13 +312,64 @@ def suite_ln():
     return ok
 
 
+def suite_dense():
+    """Strided dense layer: ragged N (lm_head), ragged K + overlapping rows (conv1 / conv2 as GEMM)."""
+    import torch.nn.functional as F
+    ok = True
+    g = torch.Generator().manual_seed(21)
+    # ---- lm_head: V not a multiple of 8
+    for (M, d, V) in [(300, 768, 5001), (8192, 768, 51865), (130, 1280, 2050)]:
+        x = torch.randn(M, d, generator=g).to(torch.bfloat16)
+        W = (torch.randn(V, d, generator=g) * 0.02).to(torch.bfloat16)
+        ldy = (V + 7) // 8 * 8
+        buf = torch.full((M, ldy), 7.0, dtype=torch.bfloat16, device=DEV)
+        ops.dense_fwd(x.to(DEV), d, 0, W.to(DEV), None, buf, ldy, 0, 1, M, d, V)
+        torch.cuda.synchronize()
+        ref = (x.to(DEV).float() @ W.to(DEV).float().t()).cpu()
+        mx, rel, _ = err_stats(buf[:, :V], ref)
+        pad = buf[:, V:]
+        pad_ok = bool(((pad == 7.0) | (pad == 0.0)).all())   # TMA clips stores at 16-byte granularity: pad columns may be zeroed
+        good = rel < 1e-2 and pad_ok
+        ok &= good
+        log(f"[dense] lm_head M={M} d={d} V={V}: rel={rel:.3g} pad 7|0={pad_ok} {'OK' if good else 'FAIL'}")
+    # ---- conv front-end
+    for (B, C, L, d) in [(2, 80, 3000, 384), (3, 80, 3000, 768), (2, 128, 3000, 1280)]:
+        x = torch.randn(B, C, L, generator=g).to(torch.bfloat16).to(DEV)
+        c1 = torch.nn.Conv1d(C, d, 3, padding=1).to(DEV).to(torch.bfloat16)
+        c2 = torch.nn.Conv1d(d, d, 3, stride=2, padding=1).to(DEV).to(torch.bfloat16)
+        pos = (torch.randn(L // 2, d, generator=g) * 0.1).to(torch.bfloat16).to(DEV)
+        with torch.no_grad():
+            r1 = F.gelu(F.conv1d(x.float(), c1.weight.float(), c1.bias.float(), padding=1))
+            ref = F.gelu(F.conv1d(r1.to(torch.bfloat16).float(), c2.weight.float(), c2.bias.float(), stride=2, padding=1))
+            ref = ref.permute(0, 2, 1) + pos.float()
+        buf1 = torch.zeros(B, L + 2, C, dtype=torch.bfloat16, device=DEV)
+        buf2 = torch.zeros(B, L + 2, d, dtype=torch.bfloat16, device=DEV)
+        buf1[:, 1:L + 1].copy_(x.transpose(1, 2))
+        W1 = c1.weight.detach().permute(0, 2, 1).reshape(d, -1).contiguous()
+        W2 = c2.weight.detach().permute(0, 2, 1).reshape(d, -1).contiguous()
+        ops.dense_fwd(buf1, C, (L + 2) * C, W1, c1.bias.detach(), buf2[:, 1:], d, (L + 2) * d, B, L, 3 * C, d, act=1)
+        h = torch.empty(B, L // 2, d, dtype=torch.bfloat16, device=DEV)
+        ops.dense_fwd(buf2, 2 * d, (L + 2) * d, W2, c2.bias.detach(), h, d, (L // 2) * d, B, L // 2, 3 * d, d, act=1,
+                      residual=pos, ldr=d, res_broadcast=True)
+        torch.cuda.synchronize()
+        _, rel1, _ = err_stats(buf2[:, 1:L + 1], r1.permute(0, 2, 1))
+        mx, rel, _ = err_stats(h, ref)
+        pads = bool((buf2[:, 0] == 0).all()) and bool((buf2[:, L + 1] == 0).all())
+        good = rel < 1e-2 and rel1 < 1e-2 and pads
+        ok &= good
+        log(f"[dense] conv front-end B={B} C={C} d={d}: conv1 rel={rel1:.3g} conv2+pos rel={rel:.3g} pads zero={pads} "
+            f"{'OK' if good else 'FAIL'}")
+    log("[dense] suite", "PASSED" if ok else "FAILED")
+    return ok
+
+
 def suite_blocks():
     """Fused Whisper blocks vs HF's own layer bodies (same RoutedLoRALinear modules) on a small geometry."""
     import speech_adapter_routing_b200 as sar
     from speech_adapter_routing_b200 import whisper_blocks
     from transformers import WhisperConfig, WhisperForConditionalGeneration
 
-    cfg = WhisperConfig(vocab_size=1000, num_mel_bins=80, d_model=384, encoder_layers=2, decoder_layers=2,
+    cfg = WhisperConfig(vocab_size=1001, num_mel_bins=80, d_model=384, encoder_layers=2, decoder_layers=2,
                         encoder_attention_heads=6, decoder_attention_heads=6, encoder_ffn_dim=1536,
                         decoder_ffn_dim=1536, max_source_positions=1500, max_target_positions=448,
                         pad_token_id=0, bos_token_id=1, eos_token_id=2, decoder_start_token_id=3)
@@ -429,21 +480,26 @@ def suite_perf2():
             it[0] += 1
             return it[0] % nbuf
         fl_qkv = 2.0 * B * T * d * 3 * d + 2.0 * B * T * r * 4 * d
-        ms = timeit(lambda: ops.attn_proj_fwd(xs[nxt()], Wqkv, bqkv, A, Bp, ia, [0, -1, 1], [0.125, 1, 1], 2, 2.0))
+        ms = timeit(lambda: ops.attn_proj_fwd(xs[nxt()], Wqkv, bqkv, A, Bp, ia, [0, -1, 1], [1, 1, 1], 2, 2.0))
         log(f"[perf2] d={d} qkv+lora fused head-major: {ms*1e3:.1f} us  {fl_qkv/ms/1e9:.1f} TFLOP/s")
-        ms = timeit(lambda: ops.attn_proj_fwd(xs[nxt()], Wqkv, bqkv, None, None, None, [-1, -1, -1], [0.125, 1, 1], 1, 2.0))
+        ms = timeit(lambda: ops.attn_proj_fwd(xs[nxt()], Wqkv, bqkv, None, None, None, [-1, -1, -1], [1, 1, 1], 1, 2.0))
         log(f"[perf2] d={d} qkv base fused head-major: {ms*1e3:.1f} us  {2.0*B*T*d*3*d/ms/1e9:.1f} TFLOP/s")
         W1 = (torch.randn(ffn, d, device=DEV) * 0.02).to(torch.bfloat16); b1 = torch.zeros(ffn, device=DEV, dtype=torch.bfloat16)
         W2 = (torch.randn(d, ffn, device=DEV) * 0.02).to(torch.bfloat16); b2 = torch.zeros(d, device=DEV, dtype=torch.bfloat16)
         Wo = (torch.randn(d, d, device=DEV) * 0.02).to(torch.bfloat16)
         fs = [torch.randn(1, B * T, ffn, device=DEV, dtype=torch.bfloat16) for _ in range(2)]
         x1 = [x.view(1, B * T, d) for x in xs]
-        ms = timeit(lambda: ops.linear_fwd(x1[nxt()], W1, b1, None, 1, out=fs[it[0] % 2]))
-        log(f"[perf2] d={d} fc1+GELU: {ms*1e3:.1f} us  {2.0*B*T*d*ffn/ms/1e9:.1f} TFLOP/s")
-        ms = timeit(lambda: ops.linear_fwd(x1[nxt()], W1, b1, None, 0, out=fs[it[0] % 2]))
-        log(f"[perf2] d={d} fc1 (no act): {ms*1e3:.1f} us  {2.0*B*T*d*ffn/ms/1e9:.1f} TFLOP/s")
-        ms = timeit(lambda: ops.linear_fwd(fs[nxt() % 2], W2, b2, x1[it[0] % nbuf], 0, out=x1[it[0] % nbuf]))
-        log(f"[perf2] d={d} fc2+residual: {ms*1e3:.1f} us  {2.0*B*T*d*ffn/ms/1e9:.1f} TFLOP/s")
+        for bn in (128, 192, 256):
+            if ffn % bn or d % bn:
+                continue
+            ms = timeit(lambda: ops.linear_fwd(x1[nxt()], W1, b1, None, 1, out=fs[it[0] % 2], block_n=bn))
+            log(f"[perf2] d={d} bn={bn} fc1+GELU: {ms*1e3:.1f} us  {2.0*B*T*d*ffn/ms/1e9:.1f} TFLOP/s")
+            ms = timeit(lambda: ops.linear_fwd(x1[nxt()], W1, b1, None, 0, out=fs[it[0] % 2], block_n=bn))
+            log(f"[perf2] d={d} bn={bn} fc1 (no act): {ms*1e3:.1f} us  {2.0*B*T*d*ffn/ms/1e9:.1f} TFLOP/s")
+            ms = timeit(lambda: ops.linear_fwd(fs[nxt() % 2], W2, b2, x1[it[0] % nbuf], 0, out=x1[it[0] % nbuf], block_n=bn))
+            log(f"[perf2] d={d} bn={bn} fc2+residual: {ms*1e3:.1f} us  {2.0*B*T*d*ffn/ms/1e9:.1f} TFLOP/s")
+            ms = timeit(lambda: ops.linear_fwd(x1[nxt()], Wo, b2, None, 0, block_n=bn))
+            log(f"[perf2] d={d} bn={bn} plain d->d: {ms*1e3:.1f} us  {2.0*B*T*d*d/ms/1e9:.1f} TFLOP/s")
         ms = timeit(lambda: F.linear(fs[nxt() % 2], W2, b2))
         log(f"[perf2] d={d} cuBLAS fc2: {ms*1e3:.1f} us  {2.0*B*T*d*ffn/ms/1e9:.1f} TFLOP/s")
         hm = [x.view(B, d // 64, T, 64) for x in xs]
