@@ -18,9 +18,9 @@
 // instructions: ncu showed the one-size-fits-all epilogue (runtime GELU / residual / scale branches, ~2300
 // instructions per 64-column chunk) stalled on instruction fetch (stall_no_inst) and paced the tensor pipe at 30 %.
 //
-// Roles per CTA (192 threads): warp 0 TMA producer (both CTAs load their halves; completion bytes are signalled on
-// the LEADER's mbarriers), warp 1 TMEM alloc + (leader only) single-thread MMA issue with multicast commits,
-// warps 2-5 epilogue on the CTA's own 128 TMEM lanes.
+// Roles per CTA (192 threads): warps 0-3 epilogue on the CTA's own 128 TMEM lanes, warp 4 TMA producer (both CTAs
+// load their halves; completion bytes are signalled on the LEADER's mbarriers), warp 5 TMEM alloc + (leader only)
+// single-thread MMA issue with multicast commits.
 #include "sar_internal.h"
 #include "sar_ptx.cuh"
 
@@ -28,7 +28,7 @@ namespace sar {
 
 constexpr int V2_ROWS_PER_CTA = 128;
 constexpr int V2_BLOCK_K = 64;
-constexpr int V2_THREADS = 192;
+
 constexpr int V2_X_BYTES = V2_ROWS_PER_CTA * V2_BLOCK_K * 2;  // 16 KB
 constexpr int V2_U_BYTES = V2_ROWS_PER_CTA * 128;             // 16 KB
 constexpr int V2_STG_BYTES = 32 * 128;
@@ -59,22 +59,29 @@ struct K1V2Params {
 };
 
 enum : int { EPI_RES = 1, EPI_GELU = 2, EPI_SCALE = 4 };
+// Epilogue warps per CTA.  The GELU epilogue is latency-bound with one warp per SMSP (ncu: 31 % wait + 12 % MUFU
+// scoreboard stalls) and the residual epilogue waits on its global loads: two warps per TMEM lane quadrant interleave
+// their dependency chains, and each then owns at most two column chunks whose residual rows are both requested before
+// the accumulator is awaited.  Measured: fc1+GELU 488 -> 365 us, out_proj+residual (K = 768) 165 -> 137 us; with a long
+// K loop (fc2, K = 3072) the epilogue is hidden anyway and the 8-warp variant is ~8 % slower, so the host picks by K.
 
-// erf-form GELU (HF ACT2FN["gelu"], what Whisper's fc1 uses): 0.5 v (1 + erf(v / sqrt 2)).
-// erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, far below one bf16 ulp of the output): 5 FMAs + one
-// MUFU.RCP + one MUFU.EX2 per element instead of libdevice erff's two-branch ~25-instruction body.
+
+// erf-form GELU (HF ACT2FN["gelu"], what Whisper's fc1 uses): v * Phi(v), Phi(v) = 0.5 (1 + erf(v / sqrt 2)).
+// Evaluated through the identity Phi(v) = 1 / (1 + exp(-2 g(v))), g = atanh(erf(v / sqrt 2)), with g fitted by the odd
+// polynomial v (c0 + c1 v^2 + c2 v^4) on the clamped argument (minimax fit over [-8, 8], tools/fit_gelu.py):
+// max |error| of v * Phi(v) = 2.5e-5, i.e. below half a bf16 ulp of the output for |y| >= 0.0064.  Cost per element:
+// 6 fma-pipe instructions + MUFU.EX2 + MUFU.RCP; libdevice erff (or A&S 7.1.26: 13 fma-pipe instructions) made the
+// 4 epilogue warps pace the tensor pipe (ncu: 52 % tensor-active) because an SMSP issues one FFMA per 2 clk.
 __device__ __forceinline__ float gelu_erf(float v) {
-  const float z = fabsf(v) * 0.70710678118654752440f;
-  float t, e;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
-  float q = fmaf(t, 1.061405429f, -1.453152027f);
-  q = fmaf(q, t, 1.421413741f);
-  q = fmaf(q, t, -0.284496736f);
-  q = fmaf(q, t, 0.254829592f);
-  const float erf_abs = fmaf(-q * t, e, 1.0f);
-  const float hv = 0.5f * v;
-  return fmaf(hv, copysignf(erf_abs, v), hv);
+  constexpr float K = -2.0f * 1.4426950408889634f;   // exp(-2 g) = 2^(K g)
+  const float vc = fminf(fmaxf(v, -10.0f), 10.0f);   // keeps the fitted polynomial on its monotone branch
+  const float v2 = vc * vc;
+  float p = fmaf(v2, K * -0.0003515167885699055f, K * 0.037005646022542554f);
+  p = fmaf(p, v2, K * 0.7975078842850871f);
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(vc * p));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return v * r;
 }
 
 template <int BLOCK_N, bool LORA>
@@ -91,8 +98,8 @@ struct V2Smem {
   }
 };
 
-template <int BLOCK_N, bool LORA, int EPI>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(V2_THREADS, 1)
+template <int BLOCK_N, bool LORA, int EPI, int EW>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (EW + 2), 1)
 k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
             const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
             const __grid_constant__ CUtensorMap tm_y0, const __grid_constant__ CUtensorMap tm_y1,
@@ -102,6 +109,16 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
   constexpr int U_COL = 2 * BLOCK_N;   // U accumulators: set s at columns [U_COL + 64 s, U_COL + 64 s + r)
   static_assert(2 * BLOCK_N + (LORA ? 2 * 64 : 0) <= TMEM_COLS, "TMEM budget");
   static_assert(BLOCK_N % 64 == 0 && BLOCK_N <= 256, "BLOCK_N");
+  // Epilogue warps: TMEM lane quadrant q = warp % 4 is fixed by the hardware.  EW = 4, or 8 (two warps per quadrant,
+  // column chunks split even / odd, one staging buffer each) for the math-heavy GELU epilogue.
+  static_assert(EW == 4 || (EW == 8 && !LORA), "epilogue warps");
+  constexpr int NGRP = EW / 4;
+  constexpr int NBUF = EW == 8 ? 1 : 2;
+  // Warp roles: epilogue = warps 0..EW-1, TMA producer = warp EW, MMA issuer = warp EW+1.  The SMSP arbiter picks
+  // the highest warp id among eligible warps, so the two single-lane control warps — whose few instructions gate
+  // the whole tensor pipe — must sit ABOVE the math-heavy epilogue warps they share an SMSP with; with the roles the
+  // other way round every extra epilogue instruction (GELU, residual) delayed TMA and MMA issue.
+  constexpr int W_TMA = EW, W_MMA = EW + 1;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -131,7 +148,7 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
   const bool has_lora = LORA && (p.n_adapters > 0) && (p.utt_adapter != nullptr);
   const uint32_t half = p.swap_halves ? (rank ^ 1u) : rank;   // which half of every B operand this CTA supplies
 
-  if (warp == 0 && lane == 0) {
+  if (warp == W_TMA && lane == 0) {
     tma_prefetch_desc(&tm_x);
     tma_prefetch_desc(&tm_w);
     tma_prefetch_desc(&tm_y0);
@@ -147,7 +164,7 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tmem_full[i], 1);
-      mbar_init(&tmem_empty[i], 8);
+      mbar_init(&tmem_empty[i], 2 * EW);
     }
     mbar_init(u_full, 1);
     mbar_init(u_ready, 8);
@@ -155,7 +172,7 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
     mbar_init(b_empty, 1);
     fence_mbar_init();
   }
-  if (warp == 1) {
+  if (warp == W_MMA) {
     tmem_alloc_2sm(tmem_ptr, TMEM_COLS);
     tmem_relinquish_2sm();
   }
@@ -176,7 +193,7 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
   // leader-side barrier addresses as seen from this CTA (shared::cluster window of rank 0)
   auto leader_addr = [&](uint64_t* bar) { return mapa_u32(smem_u32(bar), 0); };
 
-  if (warp == 0) {
+  if (warp == W_TMA) {
     // =============================================================== TMA producer (both CTAs)
     if (lane == 0) {
       int stage = 0;
@@ -232,7 +249,7 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
+  } else if (warp == W_MMA) {
     // =============================================================== MMA issuer (leader CTA, single thread)
     if (leader && lane == 0) {
       const uint32_t idesc_main = umma_idesc_bf16(256, BLOCK_N);
@@ -312,11 +329,12 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
     }
     __syncwarp();
   } else {
-    // =============================================================== epilogue warps (2..5), both CTAs
+    // =============================================================== epilogue warps (0..EW-1), both CTAs
     const int q = warp & 3;
+    const int grp = warp >> 2;   // 0 with EW = 4; 0 / 1 with EW = 8
     const int row = q * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(q * 32) << 16;
-    uint8_t* my_stg = stg + q * (2 * V2_STG_BYTES);
+    uint8_t* my_stg = stg + warp * (NBUF * V2_STG_BYTES);
     const uint32_t sw = static_cast<uint32_t>(lane & 7);
     uint32_t tile_iter = 0, lora_units = 0, stg_idx = 0;
     const uint32_t u_ready_leader = leader_addr(u_ready);
@@ -371,52 +389,68 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
         float oscale = 1.0f;
         if constexpr ((EPI & EPI_SCALE) != 0) oscale = p.seg_scale[seg];
         const bool rows_live = (m0 + q * 32) < p.T;
-        // residual: this thread's 64 columns of chunk c are one 128-byte line; chunk 0 is requested before the wait on
-        // the accumulator, chunk c+1 while chunk c is converted, so the loads never sit on the critical path
+        // residual: the warp's 32 x 64 block of a chunk is fetched COALESCED (request j: lane i reads 16 B of row
+        // 4j + i/8 — four full 128-byte lines per request instead of 32 partial ones), parked in registers while the
+        // accumulator is awaited (first chunk) / while the previous chunk is converted, then transposed to the
+        // thread-per-row layout through the swizzled staging buffer that the output is about to overwrite anyway.
+        constexpr int NC = BLOCK_N / 64;
         uint4 rs[8];
-        const uint4* res_row = nullptr;
-        if constexpr ((EPI & EPI_RES) != 0) {
-          if (m0 + row < p.T) {
-            res_row = reinterpret_cast<const uint4*>(p.residual + static_cast<size_t>(b) * p.res_bs +
-                                                     static_cast<size_t>(m0 + row) * p.ldr + n0_seg);
+        const __nv_bfloat16* res_blk = nullptr;   // row m0 + q*32, column n0_seg of this warp's block
+        const int r_sub = lane >> 3, r_chk = lane & 7;
+        auto load_res = [&](uint4 (&dst)[8], int c) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) rs[j] = __ldg(res_row + j);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) rs[j] = make_uint4(0u, 0u, 0u, 0u);
+          for (int j = 0; j < 8; ++j) {
+            const int rr = 4 * j + r_sub;
+            dst[j] = (res_blk != nullptr && m0 + q * 32 + rr < p.T)
+                         ? __ldg(reinterpret_cast<const uint4*>(res_blk + static_cast<size_t>(rr) * p.ldr + c * 64) + r_chk)
+                         : make_uint4(0u, 0u, 0u, 0u);
           }
+        };
+        if constexpr ((EPI & EPI_RES) != 0) {
+          if (grp < NC)
+            res_blk = p.residual + static_cast<size_t>(b) * p.res_bs + static_cast<size_t>(m0 + q * 32) * p.ldr + n0_seg;
+          load_res(rs, grp);
+        }
+        uint4 rn[8];
+        if constexpr ((EPI & EPI_RES) != 0 && EW == 8) {
+          if (grp + NGRP < NC) load_res(rn, grp + NGRP);
         }
         mbar_wait(&tmem_full[buf], (tile_iter >> 1) & 1);
         tc_fence_after();
 #pragma unroll 1
-        for (int c = 0; c < BLOCK_N / 64; ++c) {
+        for (int c = grp; c < NC; c += NGRP) {
           uint32_t v0[32], v1[32];
           const uint32_t taddr = tmem_base + lane_addr + buf * BLOCK_N + c * 64;
           tmem_ld_32x32(taddr, v0);
           tmem_ld_32x32(taddr + 32, v1);
-          uint4 rn[8];
-          if constexpr ((EPI & EPI_RES) != 0) {
-            if (res_row != nullptr && c + 1 < BLOCK_N / 64) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) rn[j] = __ldg(res_row + (c + 1) * 8 + j);
-            } else {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) rn[j] = make_uint4(0u, 0u, 0u, 0u);
-            }
+          if constexpr ((EPI & EPI_RES) != 0 && EW == 4) {
+            if (c + NGRP < NC) load_res(rn, c + NGRP);
           }
-          if (lane == 0) tma_store_wait_read<1>();
-          __syncwarp();
-          tmem_ld_wait();
-          uint8_t* sbuf = my_stg + (stg_idx & 1) * V2_STG_BYTES;
-          const uint32_t srow = smem_u32(sbuf) + lane * 128;
           const uint4* bias4 = p.bias ? reinterpret_cast<const uint4*>(p.bias + n0 + c * 64) : nullptr;
+          uint4 bb[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) bb[j] = bias4 ? __ldg(bias4 + j) : make_uint4(0u, 0u, 0u, 0u);
+          // the staging buffer is reused every NBUF chunks: its previous TMA store must have finished READING it
+          if (lane == 0) tma_store_wait_read<NBUF - 1>();
+          __syncwarp();
+          uint8_t* sbuf = my_stg + (stg_idx % NBUF) * V2_STG_BYTES;
+          const uint32_t srow = smem_u32(sbuf) + lane * 128;
+          if constexpr ((EPI & EPI_RES) != 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {   // row 4j + r_sub, 16-byte chunk r_chk, 128B-swizzled like the output
+              const uint32_t rr = static_cast<uint32_t>(4 * j + r_sub);
+              st_shared_v4(smem_u32(sbuf) + rr * 128 + ((static_cast<uint32_t>(r_chk) ^ (rr & 7u)) << 4), rs[j].x, rs[j].y,
+                           rs[j].z, rs[j].w);
+            }
+            __syncwarp();
+          }
+          tmem_ld_wait();
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
-            uint32_t bw[4] = {0u, 0u, 0u, 0u};
-            if (bias4) {
-              const uint4 bb = __ldg(bias4 + j);
-              bw[0] = bb.x; bw[1] = bb.y; bw[2] = bb.z; bw[3] = bb.w;
-            }
+            const uint32_t bw[4] = {bb[j].x, bb[j].y, bb[j].z, bb[j].w};
+            uint32_t rw[4] = {0u, 0u, 0u, 0u};
+            const uint32_t saddr = srow + ((static_cast<uint32_t>(j) ^ sw) << 4);
+            if constexpr ((EPI & EPI_RES) != 0) ld_shared_v4(saddr, rw[0], rw[1], rw[2], rw[3]);
             uint32_t pk[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
@@ -433,13 +467,12 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
                 a1 *= oscale;
               }
               if constexpr ((EPI & EPI_RES) != 0) {
-                const uint32_t rw = i == 0 ? rs[j].x : (i == 1 ? rs[j].y : (i == 2 ? rs[j].z : rs[j].w));
-                a0 += __uint_as_float(rw << 16);
-                a1 += __uint_as_float(rw & 0xFFFF0000u);
+                a0 += __uint_as_float(rw[i] << 16);
+                a1 += __uint_as_float(rw[i] & 0xFFFF0000u);
               }
               pk[i] = pack_bf16x2(a0, a1);
             }
-            st_shared_v4(srow + ((static_cast<uint32_t>(j) ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
+            st_shared_v4(saddr, pk[0], pk[1], pk[2], pk[3]);
           }
           if constexpr ((EPI & EPI_RES) != 0) {
 #pragma unroll
@@ -458,7 +491,7 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
         }
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(tmem_empty_leader[buf]);
+        if (lane == 0) mbar_arrive_cluster_relaxed(tmem_empty_leader[buf]);
       }
       g += LORA ? static_cast<long long>(nt_last - nt_first) : g_stride;
     }
@@ -468,14 +501,14 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
 
   tc_fence_before();
   cluster_sync_all();   // neither CTA may free TMEM / exit while its peer still reads its smem or signals its barriers
-  if (warp == 1) {
+  if (warp == W_MMA) {
     tc_fence_after();
     tmem_dealloc_2sm(tmem_base, TMEM_COLS);
   }
 }
 
 // ------------------------------------------------------------------------------------------------ host
-template <int BLOCK_N, bool LORA, int EPI>
+template <int BLOCK_N, bool LORA, int EPI, int EW = 4>
 static int k1v2_launch(const K1Args& a, cudaStream_t stream) {
   using L = V2Smem<BLOCK_N, LORA>;
   const DeviceInfo& dev = device_info();
@@ -581,14 +614,14 @@ static int k1v2_launch(const K1Args& a, cudaStream_t stream) {
     }
   }
 
-  auto kern = k1v2_kernel<BLOCK_N, LORA, EPI>;
+  auto kern = k1v2_kernel<BLOCK_N, LORA, EPI, EW>;
   static thread_local int smem_set = 0;
   if (smem_set < smem_bytes) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.max_smem_optin);
     if (e != cudaSuccess) return fail_cuda(e, "k1v2: cudaFuncSetAttribute");
     smem_set = dev.max_smem_optin;
   }
-  kern<<<2 * pairs, V2_THREADS, smem_bytes, stream>>>(tm_x, tm_w, tm_a, tm_b, tm_y[0], tm_y[1], tm_y[2], p);
+  kern<<<2 * pairs, 32 * (EW + 2), smem_bytes, stream>>>(tm_x, tm_w, tm_a, tm_b, tm_y[0], tm_y[1], tm_y[2], p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail_cuda(e, "k1v2: launch");
   return SAR_OK;
@@ -600,13 +633,16 @@ static int k1v2_dispatch_epi(const K1Args& a, int epi, cudaStream_t stream) {
     case 0: return k1v2_launch<BLOCK_N, LORA, 0>(a, stream);
     case EPI_SCALE: return k1v2_launch<BLOCK_N, LORA, EPI_SCALE>(a, stream);
     case EPI_RES:
-      if constexpr (!LORA) return k1v2_launch<BLOCK_N, false, EPI_RES>(a, stream);
+      if constexpr (!LORA) {
+        if (a.d_in <= 1536) return k1v2_launch<BLOCK_N, false, EPI_RES, 8>(a, stream);
+        return k1v2_launch<BLOCK_N, false, EPI_RES, 4>(a, stream);
+      }
       break;
     case EPI_GELU:
-      if constexpr (!LORA) return k1v2_launch<BLOCK_N, false, EPI_GELU>(a, stream);
+      if constexpr (!LORA) return k1v2_launch<BLOCK_N, false, EPI_GELU, 8>(a, stream);
       break;
     case EPI_GELU | EPI_RES:
-      if constexpr (!LORA) return k1v2_launch<BLOCK_N, false, EPI_GELU | EPI_RES>(a, stream);
+      if constexpr (!LORA) return k1v2_launch<BLOCK_N, false, EPI_GELU | EPI_RES, 8>(a, stream);
       break;
     default: break;
   }

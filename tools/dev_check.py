@@ -505,6 +505,10 @@ def suite_perf2():
         hm = [x.view(B, d // 64, T, 64) for x in xs]
         ms = timeit(lambda: ops.linear_fwd(hm[nxt()], Wo, b2, xs[(it[0] + 1) % nbuf], 0, x_head_major=True))
         log(f"[perf2] d={d} out_proj head-major+residual: {ms*1e3:.1f} us  {2.0*B*T*d*d/ms/1e9:.1f} TFLOP/s")
+        ms = timeit(lambda: ops.linear_fwd(hm[nxt()], Wo, b2, None, 0, x_head_major=True))
+        log(f"[perf2] d={d} out_proj head-major (no residual): {ms*1e3:.1f} us  {2.0*B*T*d*d/ms/1e9:.1f} TFLOP/s")
+        ms = timeit(lambda: ops.linear_fwd(xs[nxt()], Wo, b2, xs[(it[0] + 1) % nbuf], 0))
+        log(f"[perf2] d={d} d->d row-major + residual: {ms*1e3:.1f} us  {2.0*B*T*d*d/ms/1e9:.1f} TFLOP/s")
         gw = torch.ones(d, device=DEV, dtype=torch.bfloat16); gb = torch.zeros(d, device=DEV, dtype=torch.bfloat16)
         ys = [torch.empty_like(x) for x in xs]
         ms = timeit(lambda: ops.layernorm_fwd(xs[nxt()], gw, gb, 1e-5, out=ys[it[0] % nbuf]))
