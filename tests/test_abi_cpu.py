@@ -19,7 +19,8 @@ def declared_functions():
 def test_header_declares_the_documented_entry_points():
     fns = declared_functions()
     for name in ["sar_version", "sar_last_error", "sar_device_ok", "sar_workspace_bytes", "sar_qv_lora_fwd",
-                 "sar_qv_lora_fwd_rows", "sar_router_fwd", "sar_qv_lora_bwd"]:
+                 "sar_qv_lora_fwd_rows", "sar_router_fwd", "sar_qv_lora_bwd", "sar_qv_lora_fwd_pair",
+                 "sar_attn_proj_fwd", "sar_linear_fwd", "sar_dense_fwd", "sar_layernorm_fwd"]:
         assert name in fns
 
 
@@ -57,6 +58,11 @@ def test_compute_calls_fail_loudly_without_a_gpu(libsar):
     assert b"no CPU fallback" in libsar.sar_last_error()
     rc = libsar.sar_router_fwd(None, 0, *([None] * 12), 1, 1, 8, 1, 1, 1, *([None] * 5), None, None)
     assert rc == _lib.SAR_ECUDA
+    assert libsar.sar_linear_fwd(None, 0, None, None, None, None, 1, 1, 64, 128, 0, 0, None) == _lib.SAR_ECUDA
+    assert libsar.sar_dense_fwd(None, 0, 0, None, None, None, 0, 0, 0, None, 0, 0, 1, 1, 64, 128, 0, 0, None) == _lib.SAR_ECUDA
+    assert libsar.sar_layernorm_fwd(None, None, None, None, 1, 64, 1e-5, None) == _lib.SAR_ECUDA
+    assert libsar.sar_attn_proj_fwd(None, 0, None, None, None, None, None, None, None, None, 1, 1, 0, 1, 1, 64, 128, 16,
+                                    0, 1.0, 0, None) == _lib.SAR_ECUDA
 
 
 def test_python_ops_refuse_cpu_tensors():

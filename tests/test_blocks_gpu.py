@@ -1,0 +1,248 @@
+"""GPU parity tests of the fused Whisper-block entry points (sar_attn_proj_fwd, sar_linear_fwd, sar_dense_fwd,
+sar_layernorm_fwd) through the C ABI against oracle/blocks.py, and of the re-bound HF layer bodies.
+
+Tolerances (bf16 storage, fp32 accumulation; written where used):
+  projections / dense layers vs the same-rounding oracle: max|err| <= 2^-7 * max|ref|
+  LayerNorm: one bf16 rounding of values of magnitude <= 8  ->  max|err| <= 2^-5 absolute
+  GELU element-wise: |err| <= 2^-8 |ref| + 4e-5  (bf16 rounding + the 2.5e-5 fit error of the logistic-form erf-GELU)
+  fused layer bodies vs HF's own bodies over the same K1 module slots: logits max|err| <= 3e-2 * max|ref|
+"""
+import pytest
+import torch
+
+from oracle import blocks as oblocks, fixtures
+from speech_adapter_routing_b200 import ops
+
+pytestmark = pytest.mark.gpu
+
+TIGHT = 2.0 ** -7
+
+
+def rel_err(y, ref):
+    y, ref = y.float().cpu(), ref.float().cpu()
+    return ((y - ref).abs().max() / ref.abs().max().clamp_min(1e-12)).item()
+
+
+def head_major_to_rows(y):
+    B, h, T, e = y.shape
+    return y.permute(0, 2, 1, 3).reshape(B, T, h * e)
+
+
+# ------------------------------------------------------------------------------------------------ sar_attn_proj_fwd
+PROJ_CASES = [
+    # name, B, T, d, r, n, segments (lora?, out scale), grid override, base_only_every
+    ("cross q", 3, 300, 768, 16, 4, [(True, 0.125)], 0, 0),
+    ("cross k|v", 3, 300, 768, 16, 4, [(False, 1.0), (True, 1.0)], 0, 0),
+    ("self q|k|v", 3, 300, 768, 16, 4, [(True, 0.125), (False, 1.0), (True, 1.0)], 0, 0),
+    ("self q|k|v, ranges start mid-unit", 3, 256, 768, 16, 4, [(True, 0.125), (False, 1.0), (True, 1.0)], 10, 0),
+    ("self q|k|v, base-only utterances", 6, 200, 768, 16, 4, [(True, 0.125), (False, 1.0), (True, 1.0)], 0, 3),
+    ("self q|k|v, no adapters at all", 2, 256, 768, 16, 0, [(False, 0.125), (False, 1.0), (False, 1.0)], 0, 0),
+    ("medium r32", 4, 200, 1024, 32, 4, [(True, 0.125), (False, 1.0), (True, 1.0)], 0, 0),
+    ("large-v3 r64, 8 adapters", 4, 130, 1280, 64, 8, [(True, 0.125), (False, 1.0), (True, 1.0)], 0, 0),
+    ("decoder length 128", 8, 128, 768, 16, 4, [(True, 0.125), (False, 1.0), (True, 1.0)], 0, 0),
+    ("tiny d=384", 4, 100, 384, 16, 2, [(True, 0.125), (False, 1.0), (True, 1.0)], 0, 0),
+    ("single frame T=1", 5, 1, 768, 16, 4, [(True, 0.125), (False, 1.0), (True, 1.0)], 0, 0),
+]
+
+
+def _proj_case(B, T, d, r, n, segs, bo, seed=4321):
+    cases = [fixtures.make_lora_case(B, T, d, d, r, max(n, 1), seed=seed + 10 * i, base_only_every=bo)
+             for i in range(len(segs))]
+    x, idx = cases[0].x, cases[0].utt_adapter
+    refs = oblocks.attn_projections(x, [c.W for c in cases], [c.bias for c in cases],
+                                    [(c.A_stack, c.B_stack) if lo else None for c, (lo, _) in zip(cases, segs)],
+                                    cases[0].scaling, idx, [s for _, s in segs], d // 64)
+    seg_set, As, Bps = [], [], []
+    for c, (lo, _) in zip(cases, segs):
+        if lo:
+            seg_set.append(len(As)); As.append(c.A_stack); Bps.append(ops.pack_lora_b(c.B_stack))
+        else:
+            seg_set.append(-1)
+    return cases, x, idx, refs, seg_set, As, Bps
+
+
+@pytest.mark.parametrize("name,B,T,d,r,n,segs,grid,bo", PROJ_CASES, ids=[c[0] for c in PROJ_CASES])
+@pytest.mark.parametrize("head_major", [True, False])
+def test_attn_proj_matches_oracle(cuda_dev, name, B, T, d, r, n, segs, grid, bo, head_major):
+    cases, x, idx, refs, seg_set, As, Bps = _proj_case(B, T, d, r, n, segs, bo)
+    dev = cuda_dev
+    W = torch.cat([c.W for c in cases], 0).to(dev)
+    bias = torch.cat([c.bias for c in cases], 0).to(dev)
+    A = torch.cat(As, 0).to(dev) if As else None
+    Bp = torch.cat(Bps, 0).to(dev) if As else None
+    ys = ops.attn_proj_fwd(x.to(dev), W, bias, A, Bp, idx.to(dev) if As else None, seg_set, [s for _, s in segs],
+                           max(len(As), 1), cases[0].scaling, y_head_major=head_major, grid=grid)
+    for y, ref in zip(ys, refs):
+        if head_major:
+            assert y.shape == (B, d // 64, T, 64)
+            assert rel_err(y, ref) <= TIGHT
+        else:
+            assert y.shape == (B, T, d)
+            assert rel_err(y, head_major_to_rows(ref)) <= TIGHT
+
+
+def test_attn_proj_full_size_utterances_are_independent(cuda_dev):
+    """BASELINE config 2 size (B=64, T=1500, d=768, 4 adapters r16): an utterance projected alone gives bit-identical
+    rows, whatever the tile-to-SM schedule of the full batch was."""
+    segs = [(True, 1.0), (False, 1.0), (True, 1.0)]
+    cases, x, idx, _, seg_set, As, Bps = _proj_case(64, 1500, 768, 16, 4, segs, 5, seed=77)
+    dev = cuda_dev
+    W = torch.cat([c.W for c in cases], 0).to(dev)
+    bias = torch.cat([c.bias for c in cases], 0).to(dev)
+    A, Bp = torch.cat(As, 0).to(dev), torch.cat(Bps, 0).to(dev)
+    full = ops.attn_proj_fwd(x.to(dev), W, bias, A, Bp, idx.to(dev), seg_set, [1.0] * 3, 2, 2.0)
+    for b in (0, 5, 31, 63):
+        one = ops.attn_proj_fwd(x[b:b + 1].to(dev), W, bias, A, Bp, idx[b:b + 1].to(dev), seg_set, [1.0] * 3, 2, 2.0)
+        for yf, yo in zip(full, one):
+            assert torch.equal(yf[b], yo[0])
+    assert all(torch.isfinite(y.float()).all() for y in full)
+
+
+def test_attn_proj_rejects_bad_arguments(cuda_dev):
+    x = torch.zeros(1, 8, 768, dtype=torch.bfloat16, device=cuda_dev)
+    W = torch.zeros(768 + 64, 768, dtype=torch.bfloat16, device=cuda_dev)   # d_out = 832 is not a multiple of 128
+    with pytest.raises(Exception, match="multiple"):
+        ops.attn_proj_fwd(x, W, None, None, None, None, [-1], [1.0], 1, 1.0)
+
+
+# ------------------------------------------------------------------------------------------------ sar_linear_fwd
+LINEAR_CASES = [
+    # name, B, T, d_in, d_out, gelu, residual, head-major x, grid, in place
+    ("plain", 2, 300, 768, 768, False, False, False, 0, False),
+    ("fc1 + GELU", 2, 300, 768, 3072, True, False, False, 0, False),
+    ("fc2 + residual, K=3072", 2, 300, 3072, 768, False, True, False, 0, False),
+    ("out_proj from SDPA layout + residual", 3, 300, 768, 768, False, True, True, 0, False),
+    ("out_proj, few pairs", 3, 256, 768, 768, False, True, True, 10, False),
+    ("flattened rows", 1, 8192, 768, 3072, True, False, False, 0, False),
+    ("large-v3 fc1", 2, 200, 1280, 5120, True, False, False, 0, False),
+    ("medium fc2", 2, 200, 4096, 1024, False, True, False, 0, False),
+    ("in-place residual", 2, 300, 768, 768, False, True, False, 0, True),
+    ("one row", 1, 1, 768, 768, False, True, False, 0, False),
+]
+
+
+@pytest.mark.parametrize("name,B,T,d_in,d_out,gelu,res,hm,grid,inplace", LINEAR_CASES, ids=[c[0] for c in LINEAR_CASES])
+def test_linear_matches_oracle(cuda_dev, name, B, T, d_in, d_out, gelu, res, hm, grid, inplace):
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, T, d_in, generator=g).to(torch.bfloat16)
+    W = (torch.randn(d_out, d_in, generator=g) * 0.02).to(torch.bfloat16)
+    b = (torch.randn(d_out, generator=g) * 0.02).to(torch.bfloat16)
+    r = torch.randn(B, T, d_out, generator=g).to(torch.bfloat16) if res else None
+    ref = oblocks.dense(x, W, b, r, gelu)
+    xd = x.to(cuda_dev)
+    if hm:
+        xd = xd.view(B, T, d_in // 64, 64).permute(0, 2, 1, 3).contiguous()
+    rd = None if r is None else r.to(cuda_dev)
+    y = ops.linear_fwd(xd, W.to(cuda_dev), b.to(cuda_dev), rd, int(gelu), x_head_major=hm,
+                       out=rd if inplace else None, grid=grid)
+    assert y.shape == (B, T, d_out)
+    assert rel_err(y, ref) <= TIGHT
+
+
+def test_gelu_epilogue_elementwise_accuracy(cuda_dev):
+    """W = I makes the GEMM exact, so y = bf16(gelu(x)) element by element over the whole useful range and beyond."""
+    d = 128
+    v = torch.cat([torch.linspace(-12, 12, 256 * d - 8), torch.tensor([0.0, -0.0, 30.0, -30.0, 1e-3, -1e-3, 100.0, -100.0])])
+    x = v.to(torch.bfloat16).view(1, -1, d)
+    y = ops.linear_fwd(x.to(cuda_dev), torch.eye(d, dtype=torch.bfloat16, device=cuda_dev), None, None, 1).float().cpu()
+    ref = torch.nn.functional.gelu(x.float())
+    err = (y - ref).abs()
+    assert bool((err <= ref.abs() * 2.0 ** -8 + 4e-5).all()), err.max().item()
+
+
+# ------------------------------------------------------------------------------------------------ sar_dense_fwd
+@pytest.mark.parametrize("M,d,V", [(300, 768, 5001), (1024, 768, 51865), (130, 1280, 2050)])
+def test_dense_lm_head_ragged_vocab(cuda_dev, M, d, V):
+    g = torch.Generator().manual_seed(21)
+    x = torch.randn(M, d, generator=g).to(torch.bfloat16)
+    W = (torch.randn(V, d, generator=g) * 0.02).to(torch.bfloat16)
+    ldy = (V + 7) // 8 * 8
+    buf = torch.full((M + 1, ldy), 7.0, dtype=torch.bfloat16, device=cuda_dev)    # one guard row after the output
+    ops.dense_fwd(x.to(cuda_dev), d, 0, W.to(cuda_dev), None, buf, ldy, 0, 1, M, d, V)
+    ref = (x.to(cuda_dev).float() @ W.to(cuda_dev).float().t()).cpu()             # fp32 oracle evaluated on the device
+    assert rel_err(buf[:M, :V], ref) <= TIGHT
+    pad = buf[:M, V:]
+    assert bool(((pad == 7.0) | (pad == 0.0)).all())     # TMA clips stores at 16-byte granularity
+    assert bool((buf[M] == 7.0).all())                   # nothing past the last row
+
+
+@pytest.mark.parametrize("B,C,L,d", [(2, 80, 3000, 384), (3, 80, 3000, 768), (2, 128, 3000, 1280)])
+def test_dense_conv_frontend_as_gemm(cuda_dev, B, C, L, d):
+    """conv1 / conv2 of the Whisper encoder as GEMMs over overlapping rows of zero-padded channels-last frame buffers."""
+    g = torch.Generator().manual_seed(31)
+    x = torch.randn(B, C, L, generator=g).to(torch.bfloat16)
+    w1 = (torch.randn(d, C, 3, generator=g) * (C * 3) ** -0.5).to(torch.bfloat16)
+    b1 = (torch.randn(d, generator=g) * 0.1).to(torch.bfloat16)
+    w2 = (torch.randn(d, d, 3, generator=g) * (d * 3) ** -0.5).to(torch.bfloat16)
+    b2 = (torch.randn(d, generator=g) * 0.1).to(torch.bfloat16)
+    pos = (torch.randn(L // 2, d, generator=g) * 0.1).to(torch.bfloat16)
+    ref = oblocks.conv_frontend(x, w1, b1, w2, b2, pos)
+    dev = cuda_dev
+    buf1 = torch.zeros(B, L + 2, C, dtype=torch.bfloat16, device=dev)
+    buf2 = torch.zeros(B, L + 2, d, dtype=torch.bfloat16, device=dev)
+    buf1[:, 1:L + 1].copy_(x.to(dev).transpose(1, 2))
+    W1 = w1.to(dev).permute(0, 2, 1).reshape(d, -1).contiguous()
+    W2 = w2.to(dev).permute(0, 2, 1).reshape(d, -1).contiguous()
+    ops.dense_fwd(buf1, C, (L + 2) * C, W1, b1.to(dev), buf2[:, 1:], d, (L + 2) * d, B, L, 3 * C, d, act=1)
+    h = torch.empty(B, L // 2, d, dtype=torch.bfloat16, device=dev)
+    ops.dense_fwd(buf2, 2 * d, (L + 2) * d, W2, b2.to(dev), h, d, (L // 2) * d, B, L // 2, 3 * d, d, act=1,
+                  residual=pos.to(dev), ldr=d, res_broadcast=True)
+    assert rel_err(h, ref) <= TIGHT
+    assert bool((buf2[:, 0] == 0).all()) and bool((buf2[:, L + 1] == 0).all())     # the padding frames stay zero
+
+
+# ------------------------------------------------------------------------------------------------ sar_layernorm_fwd
+@pytest.mark.parametrize("M,d", [(7, 64), (1000, 384), (96000, 768), (515, 1024), (300, 1280), (33, 2048)])
+def test_layernorm_matches_oracle(cuda_dev, M, d):
+    g = torch.Generator().manual_seed(12)
+    x = (torch.randn(M, d, generator=g) * 2 + 0.5).to(torch.bfloat16)
+    w = (1 + 0.1 * torch.randn(d, generator=g)).to(torch.bfloat16)
+    b = (0.1 * torch.randn(d, generator=g)).to(torch.bfloat16)
+    y = ops.layernorm_fwd(x.to(cuda_dev), w.to(cuda_dev), b.to(cuda_dev), 1e-5)
+    ref = oblocks.layer_norm(x, w, b)
+    assert (y.float().cpu() - ref).abs().max().item() <= 2.0 ** -5
+    with pytest.raises(Exception, match="multiple of 8"):
+        ops.layernorm_fwd(torch.zeros(4, 12, dtype=torch.bfloat16, device=cuda_dev),
+                          torch.zeros(12, dtype=torch.bfloat16, device=cuda_dev),
+                          torch.zeros(12, dtype=torch.bfloat16, device=cuda_dev))
+
+
+# ------------------------------------------------------------------------------------------------ re-bound layer bodies
+def test_fused_layer_bodies_match_hf_bodies(cuda_dev):
+    """Whole model, mixed adapters incl. a base-only utterance: the fused blocks (conv-as-GEMM front-end, fused
+    projections, epilogue-fused residual / GELU, own LayerNorm, padded lm head) vs HF's bodies over the same K1 slots."""
+    import speech_adapter_routing_b200 as sar
+    from speech_adapter_routing_b200 import whisper_blocks
+    from transformers import WhisperConfig, WhisperForConditionalGeneration
+
+    cfg = WhisperConfig(vocab_size=1001, num_mel_bins=80, d_model=384, encoder_layers=2, decoder_layers=2,
+                        encoder_attention_heads=6, decoder_attention_heads=6, encoder_ffn_dim=1536,
+                        decoder_ffn_dim=1536, max_source_positions=1500, max_target_positions=448,
+                        pad_token_id=0, bos_token_id=1, eos_token_id=2, decoder_start_token_id=3)
+    torch.manual_seed(0)
+    model = WhisperForConditionalGeneration(cfg).to(torch.bfloat16).to(cuda_dev).eval()
+    langs = ["a", "b", "c"]
+    for l in langs:
+        sar.inject_lora(model, sar.LoraConfig(r=16, lora_alpha=32, target_modules=["q_proj", "v_proj"]), adapter_name=l)
+    g = torch.Generator().manual_seed(3)
+    for m in sar.lora_modules(model).values():
+        for l in langs:
+            m.lora_B[l].weight.data.copy_((torch.randn(m.out_features, 16, generator=g) * 0.05).to(cuda_dev))
+    x = torch.randn(5, 80, 3000, generator=g).to(torch.bfloat16).to(cuda_dev)
+    dec = torch.randint(4, 1001, (5, 37), generator=g).to(cuda_dev)
+    idx = torch.tensor([0, 2, -1, 1, 2], dtype=torch.int32, device=cuda_dev)
+    try:
+        with torch.no_grad(), sar.route(idx):
+            ops.reset_counters()
+            fused = model(input_features=x, decoder_input_ids=dec, use_cache=False).logits.float()
+            counts = dict(ops.LAUNCHES)
+            whisper_blocks.FUSED_BLOCKS_ENABLED = False
+            ops.reset_counters()
+            plain = model(input_features=x, decoder_input_ids=dec, use_cache=False).logits.float()
+            plain_counts = dict(ops.LAUNCHES)
+    finally:
+        whisper_blocks.FUSED_BLOCKS_ENABLED = True
+    assert counts["proj"] == 2 + 2 * 3 and counts["k1"] == 0        # 2 encoder layers x 1 + 2 decoder layers x 3
+    assert plain_counts["proj"] == 0 and plain_counts["k1"] == 12   # 2*2 + 2*4 module-slot calls
+    assert fused.shape == plain.shape == (5, 37, 1001)
+    assert rel_err(fused, plain) <= 3e-2

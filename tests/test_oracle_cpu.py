@@ -92,3 +92,45 @@ def test_language_mix_fixture_covers_every_class():
         counts = [ids.count(k) for k in range(4)]
         assert min(counts) >= 0.09 * 64, counts     # no class under ~10 % in the mixed fixtures
     assert set(fixtures.language_mix(8, 4, "single")) == {3}
+
+
+# ------------------------------------------------------------------------------------------------ oracle/blocks.py
+def test_block_oracle_reproduces_hf_encoder_layer_and_frontend():
+    """oracle.blocks is pinned against the installed HF Whisper modules themselves (fp32, CPU): composing its
+    functions the way the fused GPU path composes its kernels reproduces WhisperEncoder's front-end and one
+    WhisperEncoderLayer ($HF/models/whisper/modeling_whisper.py:626-633, :376-414), and proj_out."""
+    import torch.nn.functional as F
+    from transformers import WhisperConfig, WhisperForConditionalGeneration
+
+    from oracle import blocks as oblocks
+
+    cfg = WhisperConfig(vocab_size=203, num_mel_bins=80, d_model=128, encoder_layers=1, decoder_layers=1,
+                        encoder_attention_heads=2, decoder_attention_heads=2, encoder_ffn_dim=256, decoder_ffn_dim=256,
+                        max_source_positions=1500, max_target_positions=64, pad_token_id=0, bos_token_id=1,
+                        eos_token_id=2, decoder_start_token_id=3)
+    torch.manual_seed(5)
+    model = WhisperForConditionalGeneration(cfg).eval()
+    enc = model.model.encoder
+    x = torch.randn(2, 80, 3000)
+    with torch.no_grad():
+        h_hf = F.gelu(enc.conv2(F.gelu(enc.conv1(x)))).permute(0, 2, 1) + enc.embed_positions.weight
+        h = oblocks.conv_frontend(x, enc.conv1.weight, enc.conv1.bias, enc.conv2.weight, enc.conv2.bias,
+                                  enc.embed_positions.weight, round_mid_to_bf16=False)
+        assert torch.allclose(h, h_hf, atol=1e-5)
+        layer = enc.layers[0]
+        y_hf = layer(h_hf, None)
+        a = layer.self_attn
+        xn = oblocks.layer_norm(h, layer.self_attn_layer_norm.weight, layer.self_attn_layer_norm.bias)
+        none = torch.full((2,), -1, dtype=torch.int32)
+        q, k, v = oblocks.attn_projections(xn, [a.q_proj.weight, a.k_proj.weight, a.v_proj.weight],
+                                           [a.q_proj.bias, None, a.v_proj.bias], [None, None, None], 2.0, none,
+                                           [a.scaling, 1.0, 1.0], a.num_heads)
+        o = F.scaled_dot_product_attention(q, k, v, scale=1.0).transpose(1, 2).reshape(2, 1500, -1)
+        h1 = oblocks.dense(o, a.out_proj.weight, a.out_proj.bias, residual=h)
+        xn = oblocks.layer_norm(h1, layer.final_layer_norm.weight, layer.final_layer_norm.bias)
+        f = oblocks.dense(xn, layer.fc1.weight, layer.fc1.bias, gelu=True)
+        y = oblocks.dense(f, layer.fc2.weight, layer.fc2.bias, residual=h1)
+        # attn_projections rounds its result to bf16 (K1's output dtype): compare at bf16 resolution
+        assert (y - y_hf).abs().max().item() <= 2.0 ** -7 * y_hf.abs().max().item()
+        dec_h = torch.randn(2, 5, 128)
+        assert torch.allclose(oblocks.lm_head(dec_h, model.proj_out.weight), model.proj_out(dec_h), atol=1e-5)
