@@ -372,9 +372,10 @@ def run_b200_arm(args):
         dist.destroy_process_group()
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant K1 shape, from the ncu --set full capture
-# summarised in profiles/ (None until a capture for the current kernel exists).
-K1_DRAM_TRAFFIC_BYTES = None
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the roofline kernel (fused q|k|v + routed LoRA, M = 96000,
+# 768 -> 2304, r = 16), from the `ncu --set full` capture summarised in profiles/r01_v4_pair_kernel_ncu_full_summary.csv
+# (183.0 MB read + 399.8 MB written; algorithmic bytes = x 147.5 + y 442.4 + W 3.5 + adapters 0.3 = 593.7 MB: no re-reads).
+K1_DRAM_TRAFFIC_BYTES = 582.8e6
 
 
 def main():
