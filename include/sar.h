@@ -109,6 +109,20 @@ int sar_attn_proj_fwd(const void* x, int x_head_major, const void* W_cat, const 
                       const float* seg_scale, int n_seg, int n_sets, int y_head_major, int B, int T, int d_in,
                       int d_out, int r, int n_adapters, float scale, uint32_t flags, void* stream);
 
+/*
+ * Row-indexed form of sar_attn_proj_fwd for decode steps (one token per utterance: rows of different adapters share
+ * a tile).  The base projections of all segments run as ONE dense launch over the M rows; one gathered BGMV launch
+ * adds seg_scale[s]·(scale·x_m·A_{set,k}ᵀ)·B_{set,k}ᵀ, k = row_adapter[m], to every LoRA'd segment.
+ *   x bf16 [M, d_in];  y: n_seg pointers, each bf16 [M, d_out] (for head dim 64 this IS [M, d_out/64, 1, 64]).
+ * Replaces the q/k/v projections of WhisperAttention.forward at one token per utterance inside the reference's
+ * per-sample adapter.generate loop (src/models/adapter_router.py:744-750).
+ */
+int sar_attn_proj_fwd_rows(const void* x, const void* W_cat, const void* bias_cat, const void* A_cat,
+                           const void* Bp_cat, const int32_t* row_adapter, void* const* y,
+                           const int32_t* seg_set, const float* seg_scale, int n_seg, int n_sets, int M,
+                           int d_in, int d_out, int r, int n_adapters, float scale, uint32_t flags,
+                           void* stream);
+
 /* epilogue activations of sar_linear_fwd */
 #define SAR_ACT_NONE 0
 #define SAR_ACT_GELU 1 /* erf-form GELU, HF ACT2FN["gelu"] */

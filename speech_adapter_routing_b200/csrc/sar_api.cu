@@ -154,6 +154,28 @@ int sar_attn_proj_fwd(const void* x, int x_head_major, const void* W_cat, const 
   return attn_proj_fwd(a, static_cast<cudaStream_t>(stream));
 }
 
+int sar_attn_proj_fwd_rows(const void* x, const void* W_cat, const void* bias_cat, const void* A_cat,
+                           const void* Bp_cat, const int32_t* row_adapter, void* const* y, const int32_t* seg_set,
+                           const float* seg_scale, int n_seg, int n_sets, int M, int d_in, int d_out, int r,
+                           int n_adapters, float scale, uint32_t flags, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  if (!y || !seg_set || !seg_scale || n_seg < 1 || n_seg > 3)
+    return fail(SAR_EINVAL, "sar_attn_proj_fwd_rows: bad segments");
+  K1Args a{};
+  a.x = x; a.W = W_cat; a.bias = bias_cat; a.A_stack = A_cat; a.Bp_stack = Bp_cat;
+  a.d_in = d_in; a.d_out = d_out; a.r = r; a.n_adapters = n_adapters; a.scale = scale;
+  a.block_n_override = static_cast<int>((flags >> 8) & 0x3FF);
+  a.grid_override = static_cast<int>((flags >> 18) & 0x3FF);
+  a.n_seg = n_seg; a.n_sets = n_sets;
+  for (int s = 0; s < 3; ++s) {
+    a.seg_set[s] = s < n_seg ? seg_set[s] : -1;
+    a.seg_scale[s] = s < n_seg ? seg_scale[s] : 1.0f;
+    a.y_seg[s] = s < n_seg ? y[s] : nullptr;
+  }
+  return attn_proj_fwd_rows(a, row_adapter, M, static_cast<cudaStream_t>(stream));
+}
+
 int sar_qv_lora_fwd_pair(const void* x, const void* W_cat, const void* bias_cat, const void* A_cat,
                          const void* Bp_cat, const int32_t* utt_adapter, void* y_q, void* y_v, int B, int T, int d_in,
                          int d_out, int r, int n_adapters, float scale, uint32_t flags, void* stream) {

@@ -466,6 +466,14 @@ class AdapterRouter(nn.Module):
             idx = torch.full((B,), self.lang_to_idx[language], dtype=torch.int32, device=dev)
         else:
             idx = self.detect_indices(self.extract_encoder_features(input_features)).idx
+        from .decode import greedy_decoder_for, plan_greedy
+
+        native = greedy_decoder_for(self.whisper)
+        plan = plan_greedy(self.whisper, input_features, kwargs) if native.supported() else None
+        if plan is not None:
+            # one CUDA-graph'd token step for the whole mixed-language batch (decode.py)
+            ids = native.generate(input_features, plan, idx)
+            return _zero_pad_after_eos(ids, plan.eos_ids, first_is_prompt=False)
         was_ckpt = self.whisper.model.encoder.gradient_checkpointing
         if was_ckpt:
             self.whisper.gradient_checkpointing_disable()
@@ -481,15 +489,17 @@ class AdapterRouter(nn.Module):
         return _zero_pad_after_eos(ids, self.whisper.generation_config.eos_token_id)
 
 
-def _zero_pad_after_eos(ids: torch.Tensor, eos_token_id) -> torch.Tensor:
-    """Per-sample generation stops at the first EOS (kept); the reference then right-pads with 0 (:753-761)."""
-    if eos_token_id is None:
+def _zero_pad_after_eos(ids: torch.Tensor, eos_token_id, first_is_prompt: bool = False) -> torch.Tensor:
+    """Per-sample generation stops at the first EOS (kept); the reference then right-pads with 0 (:753-761).
+    HF's Whisper ``generate`` returns the NEW tokens only, so every position may hold a genuine EOS."""
+    if eos_token_id is None or (isinstance(eos_token_id, (list, tuple)) and not eos_token_id):
         return ids
     eos_ids = eos_token_id if isinstance(eos_token_id, (list, tuple)) else [eos_token_id]
     is_eos = torch.zeros_like(ids, dtype=torch.bool)
     for e in eos_ids:
         is_eos |= ids == e
-    is_eos[:, 0] = False   # position 0 is the decoder start token
+    if first_is_prompt:
+        is_eos[:, 0] = False
     after = (is_eos.cumsum(dim=1) - is_eos.long()) > 0   # strictly after the first EOS
     out = ids.masked_fill(after, 0)
     lengths = (~after).sum(dim=1)

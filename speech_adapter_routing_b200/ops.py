@@ -176,6 +176,36 @@ def attn_proj_fwd(x: torch.Tensor, W_cat: torch.Tensor, bias_cat: Optional[torch
     return ys
 
 
+def attn_proj_fwd_rows(x: torch.Tensor, W_cat: torch.Tensor, bias_cat: Optional[torch.Tensor],
+                       A_cat: Optional[torch.Tensor], Bp_cat: Optional[torch.Tensor], row_adapter: Optional[torch.Tensor],
+                       seg_set: Sequence[int], seg_scale: Sequence[float], n_sets: int, scale: float) -> List[torch.Tensor]:
+    """Decode-step form of ``attn_proj_fwd`` (sar_attn_proj_fwd_rows): x [M, d_in], one token per utterance, adapter
+    ``row_adapter[m]`` per row.  Returns n_seg tensors [M, d_out]."""
+    _need_cuda(x, W_cat, bias_cat, A_cat, Bp_cat, row_adapter)
+    x = _bf16c(x, "x"); W_cat = _bf16c(W_cat, "W_cat"); bias_cat = _bf16c(bias_cat, "bias_cat")
+    A_cat = _bf16c(A_cat, "A_cat"); Bp_cat = _bf16c(Bp_cat, "Bp_cat")
+    n_seg = len(seg_set)
+    M, d_in = x.shape
+    d_out = W_cat.shape[0] // n_seg
+    n_adapters, r = 0, 16
+    if A_cat is not None and row_adapter is not None and any(s >= 0 for s in seg_set):
+        n_adapters, r = A_cat.shape[0] // n_sets, A_cat.shape[1]
+        if row_adapter.dtype != torch.int32 or row_adapter.numel() != M:
+            raise ValueError("row_adapter must be int32 [M]")
+        row_adapter = row_adapter.contiguous()
+    ys = [torch.empty(M, d_out, dtype=torch.bfloat16, device=x.device) for _ in range(n_seg)]
+    yp = (ctypes.c_void_p * n_seg)(*[y.data_ptr() for y in ys])
+    ss = (ctypes.c_int32 * n_seg)(*[int(s) for s in seg_set])
+    sc = (ctypes.c_float * n_seg)(*[float(s) for s in seg_scale])
+    has_lora = n_adapters > 0
+    check(lib().sar_attn_proj_fwd_rows(_ptr(x), _ptr(W_cat), _ptr(bias_cat), _ptr(A_cat) if has_lora else None,
+                                       _ptr(Bp_cat) if has_lora else None, _ptr(row_adapter) if has_lora else None,
+                                       yp, ss, sc, n_seg, n_sets if has_lora else 1, M, d_in, d_out, r, n_adapters,
+                                       float(scale), 0, _stream(x)))
+    LAUNCHES["proj"] += 2 if has_lora else 1
+    return ys
+
+
 def linear_fwd(x: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], residual: Optional[torch.Tensor] = None,
                act: int = _lib.SAR_ACT_NONE, x_head_major: bool = False, out: Optional[torch.Tensor] = None,
                block_n: int = 0, grid: int = 0) -> torch.Tensor:

@@ -94,6 +94,16 @@ class WhisperLoRA(nn.Module):
             self.model.base_model.model.gradient_checkpointing_disable()
             self.model.config.use_cache = True
         try:
+            # short-form greedy decoding runs as one CUDA graph per token step (decode.py); beam search, sampling,
+            # timestamps ... keep HF's loop.  Like the reference, `language` / `task` are accepted and not forwarded.
+            from .decode import greedy_decoder_for, plan_greedy
+
+            hf = self.model.base_model.model
+            native = greedy_decoder_for(hf)
+            call = dict(kwargs, max_new_tokens=max_new_tokens, num_beams=num_beams)
+            plan = plan_greedy(hf, input_features, call) if native.supported() else None
+            if plan is not None:
+                return native.generate(input_features, plan)
             return self.model.generate(input_features=input_features, max_new_tokens=max_new_tokens,
                                        num_beams=num_beams, **kwargs)
         finally:

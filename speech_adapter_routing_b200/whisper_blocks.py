@@ -111,6 +111,15 @@ class _ProjPack:
 
     def __call__(self, x: torch.Tensor, idx: Optional[torch.Tensor]) -> List[torch.Tensor]:
         lora = idx is not None and self.A is not None
+        B, T, d = x.shape
+        if T == 1 and B > 1:
+            # decode step: one token per utterance — rows of different adapters share a tile (base GEMM over the B
+            # rows + gathered BGMV); [B, d_out] is bit-for-bit the head-major [B, h, 1, 64] layout
+            ys = ops.attn_proj_fwd_rows(x.view(B, d), self.W, self.bias, self.A if lora else None,
+                                        self.Bp if lora else None, idx if lora else None,
+                                        self.seg_set if lora else [-1] * len(self.seg_set), self.kernel_scale,
+                                        self.n_sets if lora else 1, self.scale)
+            return [y.view(B, -1, 1, 64) for y in ys]
         return ops.attn_proj_fwd(x, self.W, self.bias, self.A if lora else None, self.Bp if lora else None,
                                  idx if lora else None, self.seg_set if lora else [-1] * len(self.seg_set),
                                  self.kernel_scale, self.n_sets if lora else 1, self.scale, y_head_major=True)
@@ -176,6 +185,9 @@ def _dense(x: torch.Tensor, pack: _DensePack, residual: Optional[torch.Tensor] =
     """act(x·Wᵀ + b) + residual.  Row-major inputs are flattened to one [1, B·T, d] "utterance" (no LoRA term, so
     tiles may span utterances: no padding rows when T is not a multiple of the 256-row pair tile)."""
     p = pack.get()
+    if head_major and x.shape[2] == 1:      # decode step: [B, h, 1, 64] is already row-major [B, 1, d]
+        x = x.reshape(x.shape[0], 1, -1)
+        head_major = False
     if head_major:
         return ops.linear_fwd(x, p.W, p.b, residual, act, x_head_major=True, out=residual if inplace else None)
     B, T, d = x.shape
