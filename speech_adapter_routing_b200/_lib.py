@@ -17,7 +17,7 @@ LIB_PATH = CSRC_DIR / "libsar.so"
 
 SAR_OK, SAR_EINVAL, SAR_EARCH, SAR_ECUDA, SAR_EWORKSPACE = 0, -1, -2, -3, -4
 SAR_FLAG_SAVE_U = 1
-SAR_OP_QV_LORA_FWD, SAR_OP_ROUTER_FWD, SAR_OP_QV_LORA_BWD, SAR_OP_QV_LORA_FWD_ROWS = 0, 1, 2, 3
+SAR_OP_QV_LORA_FWD, SAR_OP_ROUTER_FWD, SAR_OP_QV_LORA_BWD, SAR_OP_QV_LORA_FWD_ROWS, SAR_OP_ATTN_PROJ_FWD = 0, 1, 2, 3, 4
 SAR_RPAD = 64
 SAR_ACT_NONE, SAR_ACT_GELU = 0, 1
 
@@ -28,7 +28,7 @@ _SIGNATURES = {
     "sar_device_ok": (c_int, []),
     "sar_workspace_bytes": (c_int64, [c_int, c_int64, c_int64, c_int64, c_int64, c_int64]),
     "sar_qv_lora_fwd": (c_int, [c_void_p] * 5 + [c_void_p, c_void_p, c_void_p] + [c_int] * 6 + [c_float, c_uint32, c_void_p]),
-    "sar_attn_proj_fwd": (c_int, [c_void_p, c_int] + [c_void_p] * 8 + [c_int] * 9 + [c_float, c_uint32, c_void_p]),
+    "sar_attn_proj_fwd": (c_int, [c_void_p, c_int] + [c_void_p] * 8 + [c_int] * 9 + [c_float, c_uint32, c_void_p, c_void_p]),
     "sar_attn_proj_fwd_rows": (c_int, [c_void_p] * 9 + [c_int] * 7 + [c_float, c_uint32, c_void_p]),
     "sar_qv_lora_fwd_pair": (c_int, [c_void_p] * 8 + [c_int] * 6 + [c_float, c_uint32, c_void_p]),
     "sar_linear_fwd": (c_int, [c_void_p, c_int] + [c_void_p] * 4 + [c_int] * 5 + [c_uint32, c_void_p]),

@@ -56,6 +56,8 @@ struct K1V2Params {
   long long ldr, res_bs;           // residual row stride / batch stride in elements (res_bs = 0: broadcast over b)
   int act;                         // SAR_ACT_*: 0 none, 1 erf-GELU applied to (acc + bias) before the residual
   __nv_bfloat16* u_out;
+  int u_only;        // LORA kernels: compute and save U = scale·X·A_kᵀ only (no output tiles): the split path's first launch
+  int u_ld;          // > 0: u_out is [B, T, u_ld] with set s at columns [64 s, 64 s + r); 0: legacy [B*T, r], set 0 only
 };
 
 enum : int { EPI_RES = 1, EPI_GELU = 2, EPI_SCALE = 4 };
@@ -98,7 +100,7 @@ struct V2Smem {
   }
 };
 
-template <int BLOCK_N, bool LORA, int EPI, int EW>
+template <int BLOCK_N, bool LORA, int EPI, int EW, bool AUG>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(32 * (EW + 2), 1)
 k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
             const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
@@ -112,6 +114,7 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
   // Epilogue warps: TMEM lane quadrant q = warp % 4 is fixed by the hardware.  EW = 4, or 8 (two warps per quadrant,
   // column chunks split even / odd, one staging buffer each) for the math-heavy GELU epilogue.
   static_assert(EW == 4 || (EW == 8 && !LORA), "epilogue warps");
+  static_assert(!(AUG && LORA), "AUG (low-rank term as one extra K block fed from a precomputed U) is a dense-kernel mode");
   constexpr int NGRP = EW / 4;
   constexpr int NBUF = EW == 8 ? 1 : 2;
   // Warp roles: epilogue = warps 0..EW-1, TMA producer = warp EW, MMA issuer = warp EW+1.  The SMSP arbiter picks
@@ -145,7 +148,7 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
   const int pair = blockIdx.x >> 1;
-  const bool has_lora = LORA && (p.n_adapters > 0) && (p.utt_adapter != nullptr);
+  const bool has_lora = (LORA || AUG) && (p.n_adapters > 0) && (p.utt_adapter != nullptr);
   const uint32_t half = p.swap_halves ? (rank ^ 1u) : rank;   // which half of every B operand this CTA supplies
 
   if (warp == W_TMA && lane == 0) {
@@ -242,9 +245,32 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
         const int m0 = (unit - b * p.tiles_per_utt) * 256 + rank * V2_ROWS_PER_CTA;
         int k = has_lora ? p.utt_adapter[b] : -1;
         if (k < 0 || k >= p.n_adapters) k = -1;
-        if (k >= 0 && nt_first > 0) k_loop(b, m0, k, -1, true, -1);   // U-only pass
-        for (int nt = nt_first; nt < nt_last; ++nt)
-          k_loop(b, m0, k, nt, k >= 0 && nt == 0, k >= 0 ? p.seg_set[nt / NTS] : -1);
+        if constexpr (LORA) {
+          if (k >= 0 && (nt_first > 0 || p.u_only)) k_loop(b, m0, k, -1, true, -1);   // U-only pass
+          if (!p.u_only)
+            for (int nt = nt_first; nt < nt_last; ++nt)
+              k_loop(b, m0, k, nt, k >= 0 && nt == 0, k >= 0 ? p.seg_set[nt / NTS] : -1);
+        } else {
+          k_loop(b, m0, -1, nt_first, false, -1);
+          if constexpr (AUG) {
+            // low-rank term as ONE extra K block: X slot <- the unit's rows of the precomputed U (set's 64 columns),
+            // W slot <- B_k's rows of this N tile (same 128-byte-swizzled shapes as a regular stage)
+            const int set = k >= 0 ? p.seg_set[nt_first / NTS] : -1;
+            if (set >= 0) {
+              mbar_wait(&empty[stage], phase ^ 1);
+              uint8_t* st = stages + stage * stage_bytes;
+              const uint32_t full_leader = leader_addr(&full[stage]);
+              if (leader) mbar_arrive_expect_tx(&full[stage], 2 * (V2_X_BYTES + L::WH_BYTES));
+              tma_load_3d_2sm(st, &tm_a, full_leader, set * 64, m0, b);
+              tma_load_2d_2sm(st + V2_X_BYTES, &tm_b, full_leader, 0,
+                              (set * p.n_adapters + k) * p.d_out + (nt_first % NTS) * BLOCK_N + half * (BLOCK_N / 2));
+              if (++stage == S) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          }
+        }
         g += LORA ? static_cast<long long>(nt_last - nt_first) : g_stride;
       }
     }
@@ -300,19 +326,39 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
         const int b = unit / p.tiles_per_utt;
         int k = has_lora ? p.utt_adapter[b] : -1;
         if (k < 0 || k >= p.n_adapters) k = -1;
-        if (k >= 0 && nt_first > 0) {
+        if (LORA && k >= 0 && (nt_first > 0 || p.u_only)) {
           k_loop(0, false, true);
           publish_u();
+        }
+        if (LORA && p.u_only) {
+          g += nt_last - nt_first;
+          continue;
         }
         for (int nt = nt_first; nt < nt_last; ++nt, ++tile_iter) {
           const uint32_t buf = tile_iter & 1;
           const uint32_t acc = tmem_base + buf * BLOCK_N;
           mbar_wait(&tmem_empty[buf], ((tile_iter >> 1) & 1) ^ 1);
           tc_fence_after();
-          k_loop(acc, true, k >= 0 && nt == 0);
-          if (k >= 0 && nt == 0) publish_u();
+          k_loop(acc, true, LORA && k >= 0 && nt == 0);
+          if (LORA && k >= 0 && nt == 0) publish_u();
           const int set = k >= 0 ? p.seg_set[nt / NTS] : -1;
-          if (set >= 0) {
+          if constexpr (AUG) {
+            if (set >= 0) {   // the extra K block: acc += U[:, set] · B_k[n tile]ᵀ, r/16 MMAs
+              mbar_wait(&full[stage], phase);
+              tc_fence_after();
+              const uint32_t st = smem_u32(stages + stage * stage_bytes);
+              const uint64_t ud = umma_desc_sw128(st);
+              const uint64_t bd = umma_desc_sw128(st + V2_X_BYTES);
+              const int ksteps = p.r >> 4;
+              for (int kk = 0; kk < ksteps; ++kk) umma_bf16_2sm(acc, ud + 2 * kk, bd + 2 * kk, idesc_main, 1u);
+              umma_commit_2sm(&empty[stage], 0b11);
+              if (++stage == S) {
+                stage = 0;
+                phase ^= 1;
+              }
+            }
+          }
+          if (LORA && set >= 0) {
             mbar_wait(b_full, b_uses & 1);
             tc_fence_after();
             const uint64_t ud = umma_desc_sw128(u_desc_base + set * V2_U_BYTES);
@@ -348,13 +394,14 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
       const int m0 = (unit - b * p.tiles_per_utt) * 256 + rank * V2_ROWS_PER_CTA;
       int k = has_lora ? p.utt_adapter[b] : -1;
       if (k < 0 || k >= p.n_adapters) k = -1;
-      if (k >= 0) {
+      if (LORA && k >= 0) {
         // ---- U: TMEM fp32 -> scale -> bf16 -> swizzled smem A-operand tile of THIS CTA (+ optional global save)
         mbar_wait(u_full, lora_units & 1);
         tc_fence_after();
         // the unit's rows are saved exactly once: by the range that owns its N-tile 0 (single-set calls only)
         const bool save = (p.u_out != nullptr) && (nt_first == 0) && (m0 + row < p.T);
-        uint4* u_dst = save ? reinterpret_cast<uint4*>(p.u_out + (static_cast<size_t>(b) * p.T + m0 + row) * p.r)
+        const size_t u_row_ld = p.u_ld > 0 ? static_cast<size_t>(p.u_ld) : static_cast<size_t>(p.r);
+        uint4* u_dst = save ? reinterpret_cast<uint4*>(p.u_out + (static_cast<size_t>(b) * p.T + m0 + row) * u_row_ld)
                             : nullptr;
         for (int s = 0; s < p.n_sets; ++s) {
           const uint32_t u_row = smem_u32(u_tile) + s * V2_U_BYTES + row * 128;
@@ -368,9 +415,10 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
               pk[i] = pack_bf16x2(__uint_as_float(v[2 * i]) * p.scale, __uint_as_float(v[2 * i + 1]) * p.scale);
             st_shared_v4(u_row + (((2 * j) ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
             st_shared_v4(u_row + (((2 * j + 1) ^ sw) << 4), pk[4], pk[5], pk[6], pk[7]);
-            if (save && s == 0) {
-              u_dst[2 * j] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-              u_dst[2 * j + 1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            if (save && (s == 0 || p.u_ld > 0)) {   // u_ld layout: set s occupies columns [64 s, 64 s + r)
+              uint4* ud = u_dst + (p.u_ld > 0 ? 8 * s : 0);
+              ud[2 * j] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              ud[2 * j + 1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
             }
           }
         }
@@ -379,6 +427,10 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
         __syncwarp();
         if (lane == 0) mbar_arrive_cluster(u_ready_leader);
         ++lora_units;
+      }
+      if (LORA && p.u_only) {
+        g += nt_last - nt_first;
+        continue;
       }
       for (int nt = nt_first; nt < nt_last; ++nt, ++tile_iter) {
         const uint32_t buf = tile_iter & 1;
@@ -508,11 +560,11 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
 }
 
 // ------------------------------------------------------------------------------------------------ host
-template <int BLOCK_N, bool LORA, int EPI, int EW = 4>
+template <int BLOCK_N, bool LORA, int EPI, int EW = 4, bool AUG = false>
 static int k1v2_launch(const K1Args& a, cudaStream_t stream) {
   using L = V2Smem<BLOCK_N, LORA>;
   const DeviceInfo& dev = device_info();
-  const bool has_lora = LORA;
+  const bool has_lora = LORA || AUG;
   const int n_seg = a.n_seg > 0 ? a.n_seg : 1;
   const int n_sets = (has_lora && a.n_sets > 0) ? a.n_sets : 1;
 
@@ -532,6 +584,12 @@ static int k1v2_launch(const K1Args& a, cudaStream_t stream) {
   p.y_head_major = a.y_head_major;
   p.k_blocks = (a.d_in + V2_BLOCK_K - 1) / V2_BLOCK_K;   // ragged K: columns past d_in are zero-filled by TMA
   p.n_adapters = has_lora ? a.n_adapters : 0;
+  p.u_only = (LORA && a.u_only) ? 1 : 0;
+  p.u_ld = a.u_ld;
+  if (p.u_only) {           // one "step" per unit: the roles run the U-only pass and skip the output tiles
+    p.n_tiles = 1;
+    p.nt_per_seg = 1;
+  }
   p.total_steps = static_cast<long long>(a.B) * p.tiles_per_utt * p.n_tiles;
   p.scale = a.scale;
   p.swap_halves = a.swap_halves;
@@ -545,7 +603,8 @@ static int k1v2_launch(const K1Args& a, cudaStream_t stream) {
   const uint64_t ldy = a.ldy > 0 ? a.ldy : a.d_out;
   const uint64_t y_bs = a.y_batch_stride > 0 ? a.y_batch_stride : static_cast<uint64_t>(a.T) * ldy;
   p.act = a.act;
-  p.u_out = (has_lora && n_sets == 1) ? reinterpret_cast<__nv_bfloat16*>(a.u_out) : nullptr;
+  p.u_out = (LORA && (n_sets == 1 || a.u_ld > 0)) ? reinterpret_cast<__nv_bfloat16*>(a.u_out) : nullptr;
+  if (p.u_only && (!p.u_out || a.u_ld < n_sets * 64)) return fail(SAR_EINVAL, "k1v2: U-only pass needs u_out [B,T,>=64*n_sets]");
 
   const int stage_bytes = L::stage_bytes(p.r, n_sets);
   const int budget = dev.max_smem_optin - 1024 - L::fixed_bytes(n_sets);
@@ -600,7 +659,13 @@ static int k1v2_launch(const K1Args& a, cudaStream_t stream) {
     if ((rc = make_tmap_bf16(&tm_w, a.W, 2, dims, strides, box))) return rc;
   }
   if (has_lora) {
-    {
+    if constexpr (AUG) {   // tm_a = the precomputed U, [B, T, u_ld]: one 64-column block per LoRA set
+      if (!a.u_out || a.u_ld < n_sets * 64 || a.u_ld % 8) return fail(SAR_EINVAL, "k1v2: AUG needs u [B,T,u_ld>=64*n_sets]");
+      const uint64_t dims[3] = {(uint64_t)n_sets * 64, (uint64_t)a.T, (uint64_t)a.B};
+      const uint64_t strides[2] = {(uint64_t)a.u_ld * 2, (uint64_t)a.T * a.u_ld * 2};
+      const uint32_t box[3] = {64, V2_ROWS_PER_CTA, 1};
+      if ((rc = make_tmap_bf16(&tm_a, a.u_out, 3, dims, strides, box))) return rc;
+    } else {
       const uint64_t dims[2] = {(uint64_t)a.d_in, (uint64_t)n_sets * a.n_adapters * a.r};
       const uint64_t strides[1] = {(uint64_t)a.d_in * 2};
       const uint32_t box[2] = {V2_BLOCK_K, (uint32_t)a.r / 2};
@@ -614,7 +679,7 @@ static int k1v2_launch(const K1Args& a, cudaStream_t stream) {
     }
   }
 
-  auto kern = k1v2_kernel<BLOCK_N, LORA, EPI, EW>;
+  auto kern = k1v2_kernel<BLOCK_N, LORA, EPI, EW, AUG>;
   static thread_local int smem_set = 0;
   if (smem_set < smem_bytes) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.max_smem_optin);
@@ -660,7 +725,32 @@ int k1v2_qv_lora_fwd(const K1Args& a, int block_n, cudaStream_t stream) {
       if (a.seg_scale[s] != 1.0f) epi |= EPI_SCALE;
   if (a.residual && (n_seg != 1 || a.y_head_major))
     return fail(SAR_EINVAL, "k1v2: residual needs one row-major output segment");
+  if (lora && a.u_ws != nullptr && !a.u_only) {
+    // Split path (chosen by the caller passing a workspace): launch 1 = U-only pass of the LoRA kernel, U for every set
+    // to HBM ([B,T,64*n_sets] bf16: 2-3 % of the call's traffic); launch 2 = the DENSE kernel with the low-rank term as
+    // one extra K block per tile (AUG).  Measured against the single-launch kernel that keeps U in shared memory
+    // (which is limited to 128/192-wide tiles by the TMEM budget and stalls once per unit on the U hand-over):
+    // whisper-large-v3 q|k|v r64: 1460 us -> see DESIGN.md §4.
+    if (a.residual || a.act != SAR_ACT_NONE) return fail(SAR_EINVAL, "k1v2: split LoRA path has no residual / activation");
+    const int n_sets = a.n_sets > 0 ? a.n_sets : 1;
+    K1Args u = a;
+    u.u_only = 1; u.u_out = a.u_ws; u.u_ld = 64 * n_sets; u.x_head_major = a.x_head_major;
+    int rc = k1v2_launch<128, true, 0, 4>(u, stream);
+    if (rc) return rc;
+    K1Args m = a;
+    m.u_out = a.u_ws; m.u_ld = 64 * n_sets;
+    int bn = a.block_n_override;
+    if (bn != 128 && bn != 192 && bn != 256) bn = (a.d_out % 256 == 0) ? 256 : ((a.d_out % 192 == 0) ? 192 : 128);
+    if (a.d_out % bn) return fail(SAR_EINVAL, "k1v2: d_out not divisible by BLOCK_N");
+    const bool sc = (epi & EPI_SCALE) != 0;
+    switch (bn) {
+      case 128: return sc ? k1v2_launch<128, false, EPI_SCALE, 4, true>(m, stream) : k1v2_launch<128, false, 0, 4, true>(m, stream);
+      case 192: return sc ? k1v2_launch<192, false, EPI_SCALE, 4, true>(m, stream) : k1v2_launch<192, false, 0, 4, true>(m, stream);
+      default: return sc ? k1v2_launch<256, false, EPI_SCALE, 4, true>(m, stream) : k1v2_launch<256, false, 0, 4, true>(m, stream);
+    }
+  }
   if (lora) {
+    if (block_n == 256) block_n = (a.d_out % 192 == 0) ? 192 : 128;
     switch (block_n) {
       case 128: return k1v2_dispatch_epi<128, true>(a, epi, stream);
       case 192: return k1v2_dispatch_epi<192, true>(a, epi, stream);

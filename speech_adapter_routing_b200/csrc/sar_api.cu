@@ -108,6 +108,7 @@ int64_t sar_workspace_bytes(int op, int64_t rows, int64_t T, int64_t d, int64_t 
     case SAR_OP_ROUTER_FWD: return k2_workspace_bytes(rows, T, d);
     case SAR_OP_QV_LORA_FWD_ROWS: return rows_workspace_bytes(rows, d, r);
     case SAR_OP_QV_LORA_BWD: return k3_workspace_bytes(rows, T, d, r, n);
+    case SAR_OP_ATTN_PROJ_FWD: return rows * 64 * (n > 0 ? n : 1) * 2;
     default: fail(SAR_EINVAL, "sar_workspace_bytes: unknown op"); return SAR_EINVAL;
   }
 }
@@ -132,16 +133,18 @@ int sar_qv_lora_fwd(const void* x, const void* W, const void* bias, const void* 
 int sar_attn_proj_fwd(const void* x, int x_head_major, const void* W_cat, const void* bias_cat, const void* A_cat,
                       const void* Bp_cat, const int32_t* utt_adapter, void* const* y, const int32_t* seg_set,
                       const float* seg_scale, int n_seg, int n_sets, int y_head_major, int B, int T, int d_in,
-                      int d_out, int r, int n_adapters, float scale, uint32_t flags, void* stream) {
+                      int d_out, int r, int n_adapters, float scale, uint32_t flags, void* ws, void* stream) {
   int rc = require_sm100();
   if (rc) return rc;
   if (!y || !seg_set || !seg_scale || n_seg < 1 || n_seg > 3) return fail(SAR_EINVAL, "sar_attn_proj_fwd: bad segments");
+  if (reinterpret_cast<uintptr_t>(ws) & 15) return fail(SAR_EINVAL, "sar_attn_proj_fwd: ws must be 16-byte aligned");
   K1Args a{};
   a.x = x; a.W = W_cat; a.bias = bias_cat; a.A_stack = A_cat; a.Bp_stack = Bp_cat; a.utt_adapter = utt_adapter;
   a.B = B; a.T = T; a.d_in = d_in; a.d_out = d_out; a.r = r; a.n_adapters = n_adapters; a.scale = scale;
   a.block_n_override = static_cast<int>((flags >> 8) & 0x3FF);
   a.grid_override = static_cast<int>((flags >> 18) & 0x3FF);
   a.n_seg = n_seg; a.n_sets = n_sets; a.x_head_major = x_head_major; a.y_head_major = y_head_major;
+  a.u_ws = ws;
   for (int s = 0; s < n_seg; ++s) {
     a.seg_set[s] = seg_set[s];
     a.seg_scale[s] = seg_scale[s];
@@ -183,7 +186,7 @@ int sar_qv_lora_fwd_pair(const void* x, const void* W_cat, const void* bias_cat,
   const int32_t sets[2] = {0, 1};
   const float scales[2] = {1.0f, 1.0f};
   return sar_attn_proj_fwd(x, 0, W_cat, bias_cat, A_cat, Bp_cat, utt_adapter, ys, sets, scales, 2, 2, 0, B, T, d_in,
-                           d_out, r, n_adapters, scale, flags, stream);
+                           d_out, r, n_adapters, scale, flags, nullptr, stream);
 }
 
 int sar_linear_fwd(const void* x, int x_head_major, const void* W, const void* bias, const void* residual, void* y,

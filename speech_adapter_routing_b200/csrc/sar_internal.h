@@ -63,6 +63,10 @@ struct K1Args {
   long long ldy, y_batch_stride;     // y row / batch stride in elements
   long long ldr, res_batch_stride;   // residual row stride (0 = d_out) / batch stride (0 = T*ldr)
   int res_broadcast;                 // 1: the same [T, d_out] residual for every b (positional embedding)
+  // ---- split LoRA path: U to a caller workspace, then the dense kernel with one extra K block per tile
+  void* u_ws;        // bf16 [B, T, 64*n_sets] workspace, or null = single-launch kernel (U stays in shared memory)
+  int u_only;        // internal: run only the U pass
+  int u_ld;          // internal: row stride of u_out in the [B, T, u_ld] layout
 };
 int k1_qv_lora_fwd(const K1Args& a, cudaStream_t stream);
 int k1v2_qv_lora_fwd(const K1Args& a, int block_n, cudaStream_t stream);

@@ -123,11 +123,13 @@ def attn_proj_fwd(x: torch.Tensor, W_cat: torch.Tensor, bias_cat: Optional[torch
                   A_cat: Optional[torch.Tensor], Bp_cat: Optional[torch.Tensor], utt_adapter: Optional[torch.Tensor],
                   seg_set: Sequence[int], seg_scale: Sequence[float], n_sets: int, scale: float,
                   x_head_major: bool = False, y_head_major: bool = True, block_n: int = 0,
-                  grid: int = 0) -> List[torch.Tensor]:
+                  grid: int = 0, split: bool = True) -> List[torch.Tensor]:
     """Fused attention projections (sar_attn_proj_fwd): up to three projections of the same x in one launch.
 
     x [B,T,d_in] (or [B,d_in/64,T,64] if ``x_head_major``); W_cat [n_seg*d_out, d_in]; A_cat [n_sets*n, r, d_in];
     Bp_cat [n_sets*n, d_out, 64].  Returns n_seg tensors, [B,d_out/64,T,64] if ``y_head_major`` else [B,T,d_out].
+    ``split`` (default): U = scale·x·A_kᵀ goes through a [B,T,64*n_sets] workspace and the projections run on the dense
+    256-wide kernel with one extra K block; ``split=False``: the single-launch kernel that keeps U in shared memory.
     """
     _need_cuda(x, W_cat, bias_cat, A_cat, Bp_cat, utt_adapter)
     x = _bf16c(x, "x"); W_cat = _bf16c(W_cat, "W_cat"); bias_cat = _bf16c(bias_cat, "bias_cat")
@@ -162,17 +164,20 @@ def attn_proj_fwd(x: torch.Tensor, W_cat: torch.Tensor, bias_cat: Optional[torch
     sc = (ctypes.c_float * n_seg)(*[float(s) for s in seg_scale])
     flags = ((block_n & 0x3FF) << 8) | ((grid & 0x3FF) << 18)
     has_lora = n_adapters > 0
+    ws = None
+    if has_lora and split:
+        ws = torch.empty(B * T * 64 * n_sets, dtype=torch.bfloat16, device=x.device)
 
     def launch():
         check(lib().sar_attn_proj_fwd(_ptr(x), int(x_head_major), _ptr(W_cat), _ptr(bias_cat),
                                       _ptr(A_cat) if has_lora else None, _ptr(Bp_cat) if has_lora else None,
                                       _ptr(utt_adapter) if has_lora else None, yp, ss, sc, n_seg,
                                       n_sets if has_lora else 1, int(y_head_major), B, T, d_in, d_out, r, n_adapters,
-                                      float(scale), flags, _stream(x)))
+                                      float(scale), flags, _ptr(ws), _stream(x)))
     n_lora = sum(1 for s in seg_set if s >= 0) if has_lora else 0
     flops = 2.0 * B * T * d_in * d_out * n_seg + 2.0 * B * T * r * (n_sets * d_in + n_lora * d_out) * (n_lora > 0)
     _time_k1(K1_TIMELINE, "proj", B * T, d_in, n_seg * d_out, flops, launch)
-    LAUNCHES["proj"] += 1
+    LAUNCHES["proj"] += 2 if ws is not None else 1
     return ys
 
 

@@ -62,7 +62,7 @@ def test_compute_calls_fail_loudly_without_a_gpu(libsar):
     assert libsar.sar_dense_fwd(None, 0, 0, None, None, None, 0, 0, 0, None, 0, 0, 1, 1, 64, 128, 0, 0, None) == _lib.SAR_ECUDA
     assert libsar.sar_layernorm_fwd(None, None, None, None, 1, 64, 1e-5, None) == _lib.SAR_ECUDA
     assert libsar.sar_attn_proj_fwd(None, 0, None, None, None, None, None, None, None, None, 1, 1, 0, 1, 1, 64, 128, 16,
-                                    0, 1.0, 0, None) == _lib.SAR_ECUDA
+                                    0, 1.0, 0, None, None) == _lib.SAR_ECUDA
 
 
 def test_python_ops_refuse_cpu_tensors():

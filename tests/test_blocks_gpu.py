@@ -62,8 +62,9 @@ def _proj_case(B, T, d, r, n, segs, bo, seed=4321):
 
 
 @pytest.mark.parametrize("name,B,T,d,r,n,segs,grid,bo", PROJ_CASES, ids=[c[0] for c in PROJ_CASES])
-@pytest.mark.parametrize("head_major", [True, False])
-def test_attn_proj_matches_oracle(cuda_dev, name, B, T, d, r, n, segs, grid, bo, head_major):
+@pytest.mark.parametrize("head_major,split", [(True, True), (False, True), (True, False), (False, False)])
+def test_attn_proj_matches_oracle(cuda_dev, name, B, T, d, r, n, segs, grid, bo, head_major, split):
+    """split=True: U through a workspace + dense kernel with one extra K block; split=False: single launch, U in smem."""
     cases, x, idx, refs, seg_set, As, Bps = _proj_case(B, T, d, r, n, segs, bo)
     dev = cuda_dev
     W = torch.cat([c.W for c in cases], 0).to(dev)
@@ -71,7 +72,7 @@ def test_attn_proj_matches_oracle(cuda_dev, name, B, T, d, r, n, segs, grid, bo,
     A = torch.cat(As, 0).to(dev) if As else None
     Bp = torch.cat(Bps, 0).to(dev) if As else None
     ys = ops.attn_proj_fwd(x.to(dev), W, bias, A, Bp, idx.to(dev) if As else None, seg_set, [s for _, s in segs],
-                           max(len(As), 1), cases[0].scaling, y_head_major=head_major, grid=grid)
+                           max(len(As), 1), cases[0].scaling, y_head_major=head_major, grid=grid, split=split)
     for y, ref in zip(ys, refs):
         if head_major:
             assert y.shape == (B, d // 64, T, 64)
@@ -96,6 +97,11 @@ def test_attn_proj_full_size_utterances_are_independent(cuda_dev):
         for yf, yo in zip(full, one):
             assert torch.equal(yf[b], yo[0])
     assert all(torch.isfinite(y.float()).all() for y in full)
+    # the split path (U via workspace, 256-wide dense tiles) and the single-launch path (U in shared memory, 192-wide
+    # tiles) round at the same points: identical bits
+    fused = ops.attn_proj_fwd(x.to(dev), W, bias, A, Bp, idx.to(dev), seg_set, [1.0] * 3, 2, 2.0, split=False)
+    for ys, yf in zip(full, fused):
+        assert torch.equal(ys, yf)
 
 
 def test_attn_proj_rejects_bad_arguments(cuda_dev):
@@ -242,7 +248,7 @@ def test_fused_layer_bodies_match_hf_bodies(cuda_dev):
             plain_counts = dict(ops.LAUNCHES)
     finally:
         whisper_blocks.FUSED_BLOCKS_ENABLED = True
-    assert counts["proj"] == 2 + 2 * 3 and counts["k1"] == 0        # 2 encoder layers x 1 + 2 decoder layers x 3
+    assert counts["proj"] >= 2 + 2 * 3 and counts["k1"] == 0        # >= one launch per fused projection call
     assert plain_counts["proj"] == 0 and plain_counts["k1"] == 12   # 2*2 + 2*4 module-slot calls
     assert fused.shape == plain.shape == (5, 37, 1001)
     assert rel_err(fused, plain) <= 3e-2

@@ -202,7 +202,7 @@ def _hm(y):   # [B,h,T,64] -> [B,T,h*64]
     return y.permute(0, 2, 1, 3).reshape(B, T, h * e)
 
 
-def run_proj_case(name, B, T, d, r, n, segs, grid=0, block_n=0, seed=4321, base_only_every=0):
+def run_proj_case(name, B, T, d, r, n, segs, grid=0, block_n=0, seed=4321, base_only_every=0, split=True):
     """segs: list of (lora: bool, scale) in output order; every LoRA'd segment is its own set."""
     cases = [fixtures.make_lora_case(B, T, d, d, r, max(n, 1), seed=seed + 10 * i, base_only_every=base_only_every)
              for i in range(len(segs))]
@@ -224,7 +224,7 @@ def run_proj_case(name, B, T, d, r, n, segs, grid=0, block_n=0, seed=4321, base_
     ok = True
     for hm in (True, False):
         ys = ops.attn_proj_fwd(x.to(DEV), W, bias, A, Bp, idx.to(DEV) if As else None, seg_set, [s for _, s in segs],
-                               max(len(As), 1), 2.0, y_head_major=hm, grid=grid, block_n=block_n)
+                               max(len(As), 1), 2.0, y_head_major=hm, grid=grid, block_n=block_n, split=split)
         torch.cuda.synchronize()
         rels = []
         for y, ref in zip(ys, refs):
@@ -253,6 +253,9 @@ def suite_proj():
     ok &= run_proj_case("q|k|v T=1500 B=8", 8, 1500, 768, 16, 4, [(True, s), (False, 1.0), (True, 1.0)])
     ok &= run_proj_case("q|k|v T=128 (decoder)", 8, 128, 768, 16, 4, [(True, s), (False, 1.0), (True, 1.0)])
     ok &= run_proj_case("q|k|v d=384 (tiny)", 4, 100, 384, 16, 2, [(True, s), (False, 1.0), (True, 1.0)])
+    ok &= run_proj_case("single-launch q|k|v", 3, 300, 768, 16, 4, [(True, s), (False, 1.0), (True, 1.0)], split=False)
+    ok &= run_proj_case("single-launch mid-unit", 3, 256, 768, 16, 4, [(True, s), (False, 1.0), (True, 1.0)], grid=10, split=False)
+    ok &= run_proj_case("single-launch r64 d1280", 4, 130, 1280, 64, 8, [(True, s), (False, 1.0), (True, 1.0)], split=False)
     log("[proj] suite", "PASSED" if ok else "FAILED")
     return ok
 
@@ -464,7 +467,7 @@ def suite_perf():
 def suite_perf2():
     """Whisper-block GEMMs / LN / SDPA at the bench shape (B=64, T=1500)."""
     import torch.nn.functional as F
-    for (d, ffn, r, n) in [(768, 3072, 16, 4), (1280, 5120, 64, 8)]:
+    for (d, ffn, r, n) in [(768, 3072, 16, 4), (1024, 4096, 32, 4), (1280, 5120, 64, 8)]:
         B, T = 64, 1500
         g = torch.Generator().manual_seed(1)
         nbuf = 3
@@ -480,8 +483,10 @@ def suite_perf2():
             it[0] += 1
             return it[0] % nbuf
         fl_qkv = 2.0 * B * T * d * 3 * d + 2.0 * B * T * r * 4 * d
-        ms = timeit(lambda: ops.attn_proj_fwd(xs[nxt()], Wqkv, bqkv, A, Bp, ia, [0, -1, 1], [1, 1, 1], 2, 2.0))
-        log(f"[perf2] d={d} qkv+lora fused head-major: {ms*1e3:.1f} us  {fl_qkv/ms/1e9:.1f} TFLOP/s")
+        ms = timeit(lambda: ops.attn_proj_fwd(xs[nxt()], Wqkv, bqkv, A, Bp, ia, [0, -1, 1], [1, 1, 1], 2, 2.0, split=False))
+        log(f"[perf2] d={d} qkv+lora single launch (U in smem): {ms*1e3:.1f} us  {fl_qkv/ms/1e9:.1f} TFLOP/s")
+        ms = timeit(lambda: ops.attn_proj_fwd(xs[nxt()], Wqkv, bqkv, A, Bp, ia, [0, -1, 1], [1, 1, 1], 2, 2.0, split=True))
+        log(f"[perf2] d={d} qkv+lora split (U pass + dense aug-K): {ms*1e3:.1f} us  {fl_qkv/ms/1e9:.1f} TFLOP/s")
         ms = timeit(lambda: ops.attn_proj_fwd(xs[nxt()], Wqkv, bqkv, None, None, None, [-1, -1, -1], [1, 1, 1], 1, 2.0))
         log(f"[perf2] d={d} qkv base fused head-major: {ms*1e3:.1f} us  {2.0*B*T*d*3*d/ms/1e9:.1f} TFLOP/s")
         W1 = (torch.randn(ffn, d, device=DEV) * 0.02).to(torch.bfloat16); b1 = torch.zeros(ffn, device=DEV, dtype=torch.bfloat16)
