@@ -64,86 +64,173 @@ struct Raw8<true> {
 
 // grid = (chunks, B); each CTA reduces `rows_per_chunk` frames of one utterance to a d-vector of
 // sum_t (x - mean_t) * rstd_t, written to partial[b][chunk][d].
+//
+// HBM-bound (one read of h).  The frames of a chunk are contiguous in memory, so a producer warp streams them through
+// a shared-memory ring with 1-D bulk async copies (cp.async.bulk, K2_ROWS_PER_STAGE frames = 12 KB per copy at
+// d = 768 bf16) that complete on mbarriers; up to S stages (72 KB) per CTA are in flight whatever the consumers'
+// register pressure — the register-prefetch version (2 frames per warp in flight, 2 CTAs/SM) reached 3.2 TB/s.
+// Each of the 8 consumer warps owns one frame of a stage: conflict-free 16-byte smem reads, two-pass fp32
+// statistics by warp shuffles, per-lane accumulation; fixed warp/frame assignment and fixed-order reductions keep the
+// result deterministic.
+constexpr int K2_ROWS_PER_STAGE = 2 * K2_WARPS;   // each consumer warp owns TWO frames of a stage (two independent chains)
+constexpr int K2_MAX_STAGES = 4;
+constexpr int K2_POOL_THREADS = K2_THREADS + 32;   // 8 consumer warps + 1 producer warp
+
+__device__ __forceinline__ uint32_t k2_smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void k2_mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(k2_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void k2_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(k2_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void k2_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(k2_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void k2_mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(k2_smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void k2_bulk_load(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(k2_smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(k2_smem_u32(bar))
+               : "memory");
+}
+
 template <int NV, bool FP32>
-__global__ void __launch_bounds__(K2_THREADS)
+__global__ void __launch_bounds__(K2_POOL_THREADS)
 k2_pool_kernel(const void* __restrict__ h, float* __restrict__ partial, int* __restrict__ done_counter, int T, int d,
-               int rows_per_chunk) {
-  extern __shared__ float red[];  // [K2_WARPS][d]
+               int rows_per_chunk, int n_stages) {
+  extern __shared__ __align__(128) uint8_t k2_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y, chunk = blockIdx.x;
   if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *done_counter = 0;
   const int t0 = chunk * rows_per_chunk;
   const int t1 = min(T, t0 + rows_per_chunk);
   const size_t esz = FP32 ? 4 : 2;
-  const uint8_t* base = reinterpret_cast<const uint8_t*>(h) + static_cast<size_t>(b) * T * d * esz;
-  const float inv_d = 1.0f / static_cast<float>(d);
+  const size_t row_bytes = static_cast<size_t>(d) * esz;
+  const size_t stage_bytes = K2_ROWS_PER_STAGE * row_bytes;
+  uint8_t* ring = k2_smem;                                                  // [n_stages][8 rows][d]
+  float* red = reinterpret_cast<float*>(k2_smem + n_stages * stage_bytes);  // [K2_WARPS][d]
+  uint64_t* full = reinterpret_cast<uint64_t*>(red + K2_WARPS * d);         // [n_stages]
+  uint64_t* empty = full + K2_MAX_STAGES;                                   // [n_stages]
+  const uint8_t* base = reinterpret_cast<const uint8_t*>(h) + (static_cast<size_t>(b) * T + t0) * row_bytes;
+  const int n_rows = t1 - t0;
+  const int n_groups = (n_rows + K2_ROWS_PER_STAGE - 1) / K2_ROWS_PER_STAGE;
 
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < n_stages; ++s) {
+      k2_mbar_init(&full[s], 1);
+      k2_mbar_init(&empty[s], K2_WARPS);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  if (warp == K2_WARPS) {
+    // ---------------------------------------------------------------- producer
+    if (lane == 0) {
+      for (int g = 0; g < n_groups; ++g) {
+        const int s = g % n_stages;
+        if (g >= n_stages) k2_mbar_wait(&empty[s], ((g / n_stages) - 1) & 1);
+        const int rows = min(K2_ROWS_PER_STAGE, n_rows - g * K2_ROWS_PER_STAGE);
+        const uint32_t bytes = static_cast<uint32_t>(rows * row_bytes);
+        k2_mbar_expect_tx(&full[s], bytes);
+        k2_bulk_load(ring + s * stage_bytes, base + static_cast<size_t>(g) * stage_bytes, bytes, &full[s]);
+      }
+    }
+    return;
+  }
+
+  // ------------------------------------------------------------------ consumers: warp w owns frame g*8 + w
+  const float inv_d = 1.0f / static_cast<float>(d);
   float acc[NV][8];
 #pragma unroll
   for (int v = 0; v < NV; ++v)
 #pragma unroll
     for (int i = 0; i < 8; ++i) acc[v][i] = 0.f;
 
-  Raw8<FP32> na[NV], nb[NV];
-  auto issue = [&](int t) {  // loads of frames t and t + K2_WARPS (the second may not exist)
-    const bool has_b = (t + K2_WARPS) < t1;
-    const uint8_t* ra = base + static_cast<size_t>(t) * d * esz;
-    const uint8_t* rb = base + static_cast<size_t>(has_b ? t + K2_WARPS : t) * d * esz;
+  for (int g = 0; g < n_groups; ++g) {
+    const int s = g % n_stages;
+    k2_mbar_wait(&full[s], (g / n_stages) & 1);
+    // frames warp and warp + 8 of this stage: the two statistic chains (24 adds + 5 shuffle rounds, twice) are
+    // independent, so their latencies overlap — ncu showed a single chain per warp stalled 50 % on wait / short_sb
+    const int r0 = g * K2_ROWS_PER_STAGE + warp, r1 = r0 + K2_WARPS;
+    const bool live0 = r0 < n_rows, live1 = r1 < n_rows;
+    if (live0) {
+      const uint8_t* row0 = ring + s * stage_bytes + warp * row_bytes;
+      const uint8_t* row1 = live1 ? row0 + K2_WARPS * row_bytes : row0;
+      float x0[NV][8], x1[NV][8];
+      float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      const int e = (v * 32 + lane) * 8;
-      if (e < d) {
-        na[v].load(ra, e);
-        nb[v].load(rb, e);
-      } else {
-        na[v].zero();
-        nb[v].zero();
+      for (int v = 0; v < NV; ++v) {
+        const int e = (v * 32 + lane) * 8;
+        if (e < d) {
+          if (FP32) {
+            const float4 a = *reinterpret_cast<const float4*>(row0 + static_cast<size_t>(e) * 4);
+            const float4 c = *reinterpret_cast<const float4*>(row0 + static_cast<size_t>(e) * 4 + 16);
+            const float4 a1 = *reinterpret_cast<const float4*>(row1 + static_cast<size_t>(e) * 4);
+            const float4 c1 = *reinterpret_cast<const float4*>(row1 + static_cast<size_t>(e) * 4 + 16);
+            x0[v][0] = a.x; x0[v][1] = a.y; x0[v][2] = a.z; x0[v][3] = a.w;
+            x0[v][4] = c.x; x0[v][5] = c.y; x0[v][6] = c.z; x0[v][7] = c.w;
+            x1[v][0] = a1.x; x1[v][1] = a1.y; x1[v][2] = a1.z; x1[v][3] = a1.w;
+            x1[v][4] = c1.x; x1[v][5] = c1.y; x1[v][6] = c1.z; x1[v][7] = c1.w;
+          } else {
+            const uint4 q0 = *reinterpret_cast<const uint4*>(row0 + static_cast<size_t>(e) * 2);
+            const uint4 q1 = *reinterpret_cast<const uint4*>(row1 + static_cast<size_t>(e) * 2);
+            const uint32_t w0[4] = {q0.x, q0.y, q0.z, q0.w};
+            const uint32_t w1[4] = {q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              x0[v][2 * i] = __uint_as_float(w0[i] << 16);
+              x0[v][2 * i + 1] = __uint_as_float(w0[i] & 0xFFFF0000u);
+              x1[v][2 * i] = __uint_as_float(w1[i] << 16);
+              x1[v][2 * i + 1] = __uint_as_float(w1[i] & 0xFFFF0000u);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) x0[v][i] = x1[v][i] = 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          sum0 += x0[v][i];
+          sum1 += x1[v][i];
+        }
       }
-    }
-  };
-
-  int t = t0 + warp;
-  if (t < t1) issue(t);
-  for (; t < t1; t += 2 * K2_WARPS) {
-    const bool has_b = (t + K2_WARPS) < t1;
-    float xa[NV][8], xb[NV][8];
+      const float mean0 = warp_sum(sum0) * inv_d, mean1 = warp_sum(sum1) * inv_d;
+      float sq0 = 0.f, sq1 = 0.f;
 #pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      na[v].to_float(xa[v]);
-      nb[v].to_float(xb[v]);
-    }
-    if (t + 2 * K2_WARPS < t1) issue(t + 2 * K2_WARPS);  // next pair in flight while this pair is reduced
-    float sa = 0.f, sb = 0.f;
+      for (int v = 0; v < NV; ++v) {
+        const bool live = (v * 32 + lane) * 8 < d;
 #pragma unroll
-    for (int v = 0; v < NV; ++v)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        sa += xa[v][i];
-        sb += xb[v][i];
+        for (int i = 0; i < 8; ++i) {
+          const float d0 = live ? x0[v][i] - mean0 : 0.f, d1 = live ? x1[v][i] - mean1 : 0.f;
+          x0[v][i] = d0;
+          x1[v][i] = d1;
+          sq0 += d0 * d0;
+          sq1 += d1 * d1;
+        }
       }
-    const float ma = warp_sum(sa) * inv_d, mb = warp_sum(sb) * inv_d;
-    float qa = 0.f, qb = 0.f;
+      const float rstd0 = 1.0f / sqrtf(warp_sum(sq0) * inv_d + K2_EPS);
+      const float rstd1 = live1 ? 1.0f / sqrtf(warp_sum(sq1) * inv_d + K2_EPS) : 0.f;
 #pragma unroll
-    for (int v = 0; v < NV; ++v) {
-      const bool live = (v * 32 + lane) * 8 < d;
+      for (int v = 0; v < NV; ++v)
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float da = live ? xa[v][i] - ma : 0.f, db = live ? xb[v][i] - mb : 0.f;
-        xa[v][i] = da;
-        xb[v][i] = db;
-        qa += da * da;
-        qb += db * db;
-      }
+        for (int i = 0; i < 8; ++i) acc[v][i] += x0[v][i] * rstd0 + x1[v][i] * rstd1;
     }
-    const float ra_std = 1.0f / sqrtf(warp_sum(qa) * inv_d + K2_EPS);
-    const float rb_std = has_b ? 1.0f / sqrtf(warp_sum(qb) * inv_d + K2_EPS) : 0.f;
-#pragma unroll
-    for (int v = 0; v < NV; ++v)
-#pragma unroll
-      for (int i = 0; i < 8; ++i) acc[v][i] += xa[v][i] * ra_std + xb[v][i] * rb_std;
+    __syncwarp();
+    if (lane == 0) k2_mbar_arrive(&empty[s]);
   }
 
-  // fixed-order cross-warp reduction
+  // fixed-order cross-warp reduction (consumer warps only: named barrier over 256 threads)
 #pragma unroll
   for (int v = 0; v < NV; ++v) {
     const int e = (v * 32 + lane) * 8;
@@ -152,13 +239,13 @@ k2_pool_kernel(const void* __restrict__ h, float* __restrict__ partial, int* __r
       for (int i = 0; i < 8; ++i) red[warp * d + e + i] = acc[v][i];
     }
   }
-  __syncthreads();
+  asm volatile("bar.sync 1, %0;" ::"n"(K2_THREADS) : "memory");
   float* out = partial + (static_cast<size_t>(b) * gridDim.x + chunk) * d;
   for (int j = threadIdx.x; j < d; j += K2_THREADS) {
-    float s = 0.f;
+    float sacc = 0.f;
 #pragma unroll
-    for (int w = 0; w < K2_WARPS; ++w) s += red[w * d + j];
-    out[j] = s;
+    for (int w = 0; w < K2_WARPS; ++w) sacc += red[w * d + j];
+    out[j] = sacc;
   }
 }
 
@@ -306,16 +393,34 @@ __global__ void __launch_bounds__(K2_THREADS) k2_head_kernel(const K2HeadParams 
     is_last = (atomicAdd(p.done_counter, 1) == p.B - 1);
   }
   __syncthreads();
-  if (is_last && threadIdx.x == 0) {
-    // stable counting sort of utterances by class: B is a batch size (<= a few thousand)
+  if (is_last) {
+    // Stable counting sort of the utterances by class, by the whole CTA (one thread walking idx[] through L2 cost
+    // ~40 us at B = 64): for each class, a ballot-based block scan over the utterances in index order.
     __threadfence();
-    int* counts = reinterpret_cast<int*>(scratch + K2_WARPS);
-    for (int c = 0; c <= p.C; ++c) counts[c] = 0;
+    __shared__ int warp_tot[K2_WARPS];
     const volatile int32_t* vidx = p.idx;
-    for (int i = 0; i < p.B; ++i) counts[vidx[i] + 1]++;
-    for (int c = 0; c < p.C; ++c) counts[c + 1] += counts[c];
-    for (int c = 0; c <= p.C; ++c) p.seg_starts[c] = counts[c];
-    for (int i = 0; i < p.B; ++i) p.perm[counts[vidx[i]]++] = i;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int running = 0;
+    for (int c = 0; c < p.C; ++c) {
+      if (threadIdx.x == 0) p.seg_starts[c] = running;
+      for (int i0 = 0; i0 < p.B; i0 += K2_THREADS) {
+        const int i = i0 + threadIdx.x;
+        const bool flag = i < p.B && vidx[i] == c;
+        const unsigned ballot = __ballot_sync(0xffffffffu, flag);
+        if (lane == 0) warp_tot[warp] = __popc(ballot);
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < K2_WARPS; ++w) {
+          before += w < warp ? warp_tot[w] : 0;
+          total += warp_tot[w];
+        }
+        if (flag) p.perm[running + before + __popc(ballot & ((1u << lane) - 1u))] = i;
+        running += total;
+        __syncthreads();
+      }
+    }
+    if (threadIdx.x == 0) p.seg_starts[p.C] = running;
   }
 }
 
@@ -326,34 +431,43 @@ int64_t k2_workspace_bytes(int64_t B, int64_t T, int64_t d) {
 }
 
 static int k2_rows_per_chunk(int B, int T, int num_sms) {
-  // Rows per CTA: a multiple of 16 (8 warps x 2 frames per iteration) in [16, 128].  Small batches get small chunks
-  // (more CTAs); large batches pick the size whose CTA count wastes the least of the last wave (2 CTAs per SM).
-  const int64_t slots = static_cast<int64_t>(num_sms) * 2;
-  int best = 16;
-  double best_cost = 1e30;
-  for (int rows = 16; rows <= 128; rows += 16) {
-    const int64_t ctas = static_cast<int64_t>(B) * ((T + rows - 1) / rows);
-    const int64_t waves = (ctas + slots - 1) / slots;
-    // time ~ waves * (rows + fixed per-CTA overhead of ~12 rows' worth of latency)
-    const double cost = static_cast<double>(waves) * (rows + 12);
-    if (cost < best_cost - 1e-9) {
-      best_cost = cost;
-      best = rows;
-    }
-  }
-  return best;
+  // One wave of long-lived CTAs (2 per SM: the shared-memory ring of each holds up to 72 KB in flight): as many chunks
+  // per utterance as fit in 2*num_sms CTAs, so every CTA streams dozens of 8-frame groups and its ring stays full.
+  // Short chunks (the register-prefetch version used 16..128 frames) pay the pipeline fill once per CTA and measured
+  // 2.3 TB/s with this kernel.
+  const int slots = num_sms * 2;
+  int chunks = slots / (B > 0 ? B : 1);
+  const int max_chunks = (T + K2_ROWS_PER_STAGE - 1) / K2_ROWS_PER_STAGE;
+  if (chunks > max_chunks) chunks = max_chunks;
+  if (chunks < 1) chunks = 1;
+  int rows = (T + chunks - 1) / chunks;
+  rows = (rows + K2_ROWS_PER_STAGE - 1) / K2_ROWS_PER_STAGE * K2_ROWS_PER_STAGE;
+  if (rows < 16) rows = 16;   // workspace sizing assumes >= 16 frames per chunk
+  return rows;
 }
 
 template <bool FP32>
 static int k2_launch_pool(const K2Args& a, float* partial, int* counter, int chunks, int rpc, cudaStream_t stream) {
   const int nv = (a.d + 255) / 256;
   const dim3 grid(chunks, a.B);
-  const size_t smem = static_cast<size_t>(K2_WARPS) * a.d * sizeof(float);
+  const DeviceInfo& dev = device_info();
+  const size_t stage_bytes = static_cast<size_t>(K2_ROWS_PER_STAGE) * a.d * (FP32 ? 4 : 2);
+  const size_t fixed = static_cast<size_t>(K2_WARPS) * a.d * sizeof(float) + 2 * K2_MAX_STAGES * sizeof(uint64_t) + 128;
+  // two CTAs per SM: each may use half of the shared memory
+  const size_t budget = static_cast<size_t>(dev.max_smem_optin) / 2 - 2048;
+  int n_stages = fixed < budget ? static_cast<int>((budget - fixed) / stage_bytes) : 0;
+  if (n_stages > K2_MAX_STAGES) n_stages = K2_MAX_STAGES;
+  if (n_stages < 2) {   // very wide fp32 rows: one CTA per SM
+    n_stages = static_cast<int>((static_cast<size_t>(dev.max_smem_optin) - 2048 - fixed) / stage_bytes);
+    if (n_stages > K2_MAX_STAGES) n_stages = K2_MAX_STAGES;
+    if (n_stages < 1) return fail(SAR_EINVAL, "k2: row too wide for the shared-memory ring");
+  }
+  const size_t smem = n_stages * stage_bytes + fixed;
 #define SAR_K2_CASE(N)                                                                                          \
   case N:                                                                                                       \
     if (smem > 48 * 1024)                                                                                       \
       cudaFuncSetAttribute(k2_pool_kernel<N, FP32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);    \
-    k2_pool_kernel<N, FP32><<<grid, K2_THREADS, smem, stream>>>(a.h, partial, counter, a.T, a.d, rpc);          \
+    k2_pool_kernel<N, FP32><<<grid, K2_POOL_THREADS, smem, stream>>>(a.h, partial, counter, a.T, a.d, rpc, n_stages); \
     break;
   switch (nv) {
     SAR_K2_CASE(1) SAR_K2_CASE(2) SAR_K2_CASE(3) SAR_K2_CASE(4) SAR_K2_CASE(5) SAR_K2_CASE(6) SAR_K2_CASE(7)
