@@ -252,3 +252,61 @@ def test_fused_layer_bodies_match_hf_bodies(cuda_dev):
     assert plain_counts["proj"] == 0 and plain_counts["k1"] == 12   # 2*2 + 2*4 module-slot calls
     assert fused.shape == plain.shape == (5, 37, 1001)
     assert rel_err(fused, plain) <= 3e-2
+
+
+# ------------------------------------------------------------------------------------------------ decode-step rows form
+@pytest.mark.parametrize("M,d,r,n,segs", [
+    (64, 768, 16, 4, [(True, 0.125), (False, 1.0), (True, 1.0)]),      # self-attention q|k|v of a decode step, B = 64
+    (5, 768, 16, 4, [(True, 0.125)]),                                   # cross-attention q
+    (130, 1280, 64, 8, [(True, 0.125), (False, 1.0), (True, 1.0)]),     # more rows than one 128-row tile half
+    (16, 1024, 32, 4, [(False, 1.0), (True, 1.0)]),
+])
+def test_attn_proj_rows_matches_oracle(cuda_dev, M, d, r, n, segs):
+    """sar_attn_proj_fwd_rows: one token per utterance, rows of different adapters (and base-only rows) share a tile."""
+    cases, x, idx, refs, seg_set, As, Bps = _proj_case(M, 1, d, r, n, segs, 5)
+    dev = cuda_dev
+    W = torch.cat([c.W for c in cases], 0).to(dev)
+    bias = torch.cat([c.bias for c in cases], 0).to(dev)
+    A, Bp = torch.cat(As, 0).to(dev), torch.cat(Bps, 0).to(dev)
+    ys = ops.attn_proj_fwd_rows(x.view(M, d).to(dev), W, bias, A, Bp, idx.to(dev), seg_set, [s for _, s in segs],
+                                len(As), cases[0].scaling)
+    for y, ref in zip(ys, refs):
+        assert y.shape == (M, d)
+        # two bf16 roundings (base GEMM result, then + low-rank update): 2^-6 instead of 2^-7
+        assert rel_err(y.view(M, d // 64, 1, 64), ref) <= 2.0 ** -6
+
+
+def test_attn_proj_large_v3_full_size(cuda_dev):
+    """BASELINE config 4 shape on one GPU (whisper-large-v3: d = 1280, 8 adapters r64, 64 clips x 1500 frames): the
+    split and single-launch paths agree bit for bit, utterances are independent, base-only utterances equal the dense
+    projection."""
+    segs = [(True, 1.0), (False, 1.0), (True, 1.0)]
+    B, T, d, r, n = 64, 1500, 1280, 64, 8
+    g = torch.Generator().manual_seed(99)
+    dev = cuda_dev
+    x = torch.randn(B, T, d, generator=g).to(torch.bfloat16).to(dev)
+    W = (torch.randn(3 * d, d, generator=g) * 0.02).to(torch.bfloat16).to(dev)
+    bias = (torch.randn(3 * d, generator=g) * 0.02).to(torch.bfloat16).to(dev)
+    A = ((torch.rand(2 * n, r, d, generator=g) * 2 - 1) * d ** -0.5).to(torch.bfloat16).to(dev)
+    Bp = ops.pack_lora_b((torch.randn(2 * n, d, r, generator=g) * 0.02).to(torch.bfloat16).to(dev))
+    idx = torch.randint(0, n, (B,), generator=g).to(torch.int32)
+    idx[::7] = -1
+    idx = idx.to(dev)
+    split = ops.attn_proj_fwd(x, W, bias, A, Bp, idx, [0, -1, 1], [1.0] * 3, 2, 2.0, split=True)
+    fused = ops.attn_proj_fwd(x, W, bias, A, Bp, idx, [0, -1, 1], [1.0] * 3, 2, 2.0, split=False)
+    dense = ops.attn_proj_fwd(x, W, bias, None, None, None, [-1, -1, -1], [1.0] * 3, 1, 2.0)
+    for ys, yf, yd in zip(split, fused, dense):
+        assert torch.equal(ys, yf)
+        assert torch.equal(ys[::7], yd[::7])                       # base-only utterances
+        assert torch.isfinite(ys.float()).all()
+    assert torch.equal(split[1], dense[1])                         # k_proj carries no adapter
+    assert not torch.equal(split[0][1], dense[0][1])               # an adapted utterance differs from the base
+    b = 33
+    one = ops.attn_proj_fwd(x[b:b + 1], W, bias, A, Bp, idx[b:b + 1], [0, -1, 1], [1.0] * 3, 2, 2.0)
+    for ys, yo in zip(split, one):
+        assert torch.equal(ys[b], yo[0])
+    # fp32 reference of one utterance's q segment, evaluated on the device
+    k = int(idx[b])
+    u = ((x[b].float() @ A[k].float().t()) * 2.0).to(torch.bfloat16).float()
+    ref = x[b].float() @ W[:d].float().t() + bias[:d].float() + (u @ Bp[k, :, :r].float().t() if k >= 0 else 0)
+    assert rel_err(head_major_to_rows(split[0][b:b + 1])[0], ref) <= TIGHT
