@@ -384,10 +384,13 @@ def run_b200_arm(args):
         dist.destroy_process_group()
 
 
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the roofline kernel (fused q|k|v + routed LoRA, M = 96000,
-# 768 -> 2304, r = 16), from the `ncu --set full` capture summarised in profiles/r01_v4_pair_kernel_ncu_full_summary.csv
-# (183.0 MB read + 399.8 MB written; algorithmic bytes = x 147.5 + y 442.4 + W 3.5 + adapters 0.3 = 593.7 MB: no re-reads).
-K1_DRAM_TRAFFIC_BYTES = 582.8e6
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE call of the roofline op (fused q|k|v + routed LoRA, M = 96000,
+# 768 -> 2304, r = 16, split path = two launches), from the `ncu --set full` capture summarised in
+# profiles/r01_v5_pair_kernel_ncu_full_summary.csv: U pass 147.7 MB read + 5.9 MB written, dense AUG kernel 178.2 MB
+# read + 390.5 MB written.  Algorithmic bytes = x 147.5 + y 442.4 + W 3.5 + adapters 0.3 = 593.7 MB; the surplus is
+# the second read of x by the U pass (the single-launch kernel that keeps U on chip moves 584 MB but runs at 52 %
+# tensor-active instead of 74 %: DESIGN.md §4).
+K1_DRAM_TRAFFIC_BYTES = 722.3e6
 
 
 def main():

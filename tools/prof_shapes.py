@@ -1,8 +1,8 @@
 """ncu driver: one launch of the pair kernel per Whisper-block GEMM shape (after one warm-up launch of each).
 
-    ncu --set full --clock-control none --import-source on -k regex:k1v2 -s 6 -c 6 -o gpurun_out/prof python tools/prof_shapes.py
+    ncu --set full --clock-control none --import-source on -k regex:k1v2 -s 8 -c 8 -o gpurun_out/prof python tools/prof_shapes.py
 Order of the profiled launches: plain 768->768 | fc1 768->3072 | fc1+GELU | out_proj head-major+residual |
-q|k|v + LoRA head-major | fc2 3072->768 + residual.
+q|k|v + LoRA split path (U pass, then dense AUG kernel) | fc2 3072->768 + residual | q|k|v + LoRA single launch.
 """
 import sys
 from pathlib import Path
@@ -39,6 +39,7 @@ def all_shapes():
     ops.linear_fwd(xh, W, bd, x2, 0, x_head_major=True)
     ops.attn_proj_fwd(x, Wqkv, bqkv, A, Bp, ia, [0, -1, 1], [1, 1, 1], 2, 2.0)
     ops.linear_fwd(f, W2, bd, x2.view(1, B * T, d))
+    ops.attn_proj_fwd(x, Wqkv, bqkv, A, Bp, ia, [0, -1, 1], [1, 1, 1], 2, 2.0, split=False)
 
 
 all_shapes()
