@@ -390,7 +390,10 @@ static int k1_launch(const K1Args& a, cudaStream_t stream) {
   }
 
   auto kern = k1_qv_lora_fwd_kernel<BLOCK_N>;
-  static thread_local int smem_set = 0;
+  // the opt-in shared-memory limit is a per-device attribute of the kernel: remember it per device (and per thread:
+  // no lock needed, the call is idempotent)
+  static thread_local int smem_set_dev[64] = {};
+  int& smem_set = smem_set_dev[dev.device & 63];
   if (smem_set < smem_bytes) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, dev.max_smem_optin);
     if (e != cudaSuccess) return fail_cuda(e, "k1: cudaFuncSetAttribute");
