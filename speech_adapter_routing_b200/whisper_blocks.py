@@ -345,7 +345,16 @@ def _encoder_forward(self, input_features, attention_mask=None, **kwargs):
                          f"Make sure to pad the input mel features to {expected}.")
     pk = self._sar_pack
     if pk["conv_ok"]:
-        h = _conv_frontend(self, x.contiguous())
+        # The front-end carries no adapter, so the LID pass and the routed pass of one AdapterRouter.forward compute the
+        # same thing from the same tensor: keep the last result, keyed on the input tensor OBJECT (held alive, so its
+        # storage cannot be recycled under us), its version counter and the conv / position parameters' versions.
+        wkey = (pk["conv1"].get().key, pk["conv2"].get().key, pk["pos"].get().key)
+        c = pk.get("conv_cache")
+        if c is not None and c[0] is x and c[1] == x._version and c[2] == wkey:
+            h = c[3]
+        else:
+            h = _conv_frontend(self, x.contiguous())
+            pk["conv_cache"] = (x, x._version, wkey, h)
     else:
         h = F.gelu(self.conv2(F.gelu(self.conv1(x)))).permute(0, 2, 1) + self.embed_positions.weight
     for layer in self.layers:
