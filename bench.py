@@ -338,7 +338,7 @@ def run_b200_arm(args):
                 "gemm_share_of_step": ms_gemm_all / ms_total if ms_total else None,
                 "algorithmic_flops_per_launch": fl / max(n_big, 1),
                 "all_tcgen05_gemms": {k: {"launches": v[0], "avg_us": 1e3 * v[1] / v[0], "tflops": v[2] / (v[1] * 1e-3) / 1e12}
-                                      for k, v in sorted(by_kind.items(), key=lambda kv: -kv[1][1])[:8]}}
+                                      for k, v in sorted(by_kind.items(), key=lambda kv: -kv[1][1])[:20]}}
 
     # ---- end to end through the public API with host buffers ------------------------------------------------
     def e2e_step(x_host):
