@@ -141,7 +141,9 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
   uint64_t* u_ready = u_full + 1;                 //      leader only (count 8)
   uint64_t* b_full = u_ready + 1;                 //      leader only (count 1 + tx of both)
   uint64_t* b_empty = b_full + 1;                 //      per CTA (multicast commit)
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_empty + 1);
+  uint64_t* u_full2 = b_empty + 1;                //      second U buffer of the U-only pass (double-buffered)
+  uint64_t* u_ready2 = u_full2 + 1;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(u_ready2 + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -171,6 +173,8 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
     }
     mbar_init(u_full, 1);
     mbar_init(u_ready, 8);
+    mbar_init(u_full2, 1);
+    mbar_init(u_ready2, 8);
     mbar_init(b_full, 1);
     mbar_init(b_empty, 1);
     fence_mbar_init();
@@ -285,6 +289,7 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
       int stage = 0;
       uint32_t phase = 0;
       uint32_t tile_iter = 0, lora_units = 0, b_uses = 0;
+      uint32_t u_col = U_COL;   // TMEM column of U set 0 (the U-only pass alternates between two buffers)
       auto k_loop = [&](uint32_t acc, bool main, bool with_a) {
         for (int kb = 0; kb < KB; ++kb) {
           mbar_wait(&full[stage], phase);
@@ -302,7 +307,7 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
               const uint64_t ad = umma_desc_sw128(st + V2_X_BYTES + L::WH_BYTES + s * ah_slot);
 #pragma unroll
               for (int kk = 0; kk < V2_BLOCK_K / 16; ++kk)
-                umma_bf16_2sm(tmem_base + U_COL + 64 * s, xd + 2 * kk, ad + 2 * kk, idesc_u, (kb | kk) != 0);
+                umma_bf16_2sm(tmem_base + u_col + 64 * s, xd + 2 * kk, ad + 2 * kk, idesc_u, (kb | kk) != 0);
             }
           }
           umma_commit_2sm(&empty[stage], 0b11);
@@ -326,13 +331,26 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
         const int b = unit / p.tiles_per_utt;
         int k = has_lora ? p.utt_adapter[b] : -1;
         if (k < 0 || k >= p.n_adapters) k = -1;
-        if (LORA && k >= 0 && (nt_first > 0 || p.u_only)) {
-          k_loop(0, false, true);
-          publish_u();
-        }
         if (LORA && p.u_only) {
+          // U-only pass: two U buffers in TMEM (the accumulator columns are free), so the MMAs of unit j+1 run while the
+          // epilogue warps convert and store unit j; a buffer is re-used once its previous conversion has arrived
+          if (k >= 0) {
+            const uint32_t ub = lora_units & 1, nb = lora_units >> 1;
+            if (nb >= 1) {
+              mbar_wait(ub ? u_ready2 : u_ready, (nb - 1) & 1);
+              tc_fence_after();
+            }
+            u_col = ub ? 0u : static_cast<uint32_t>(U_COL);
+            k_loop(0, false, true);
+            umma_commit_2sm(ub ? u_full2 : u_full, 0b11);
+            ++lora_units;
+          }
           g += nt_last - nt_first;
           continue;
+        }
+        if (LORA && k >= 0 && nt_first > 0) {
+          k_loop(0, false, true);
+          publish_u();
         }
         for (int nt = nt_first; nt < nt_last; ++nt, ++tile_iter) {
           const uint32_t buf = tile_iter & 1;
@@ -384,6 +402,7 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
     const uint32_t sw = static_cast<uint32_t>(lane & 7);
     uint32_t tile_iter = 0, lora_units = 0, stg_idx = 0;
     const uint32_t u_ready_leader = leader_addr(u_ready);
+    const uint32_t u_ready2_leader = leader_addr(u_ready2);
     const uint32_t tmem_empty_leader[2] = {leader_addr(&tmem_empty[0]), leader_addr(&tmem_empty[1])};
     long long g = g0;
     while (g < g1) {
@@ -396,7 +415,10 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
       if (k < 0 || k >= p.n_adapters) k = -1;
       if (LORA && k >= 0) {
         // ---- U: TMEM fp32 -> scale -> bf16 -> swizzled smem A-operand tile of THIS CTA (+ optional global save)
-        mbar_wait(u_full, lora_units & 1);
+        // (U-only pass: alternating TMEM buffers / barriers, see the MMA issuer)
+        const bool second = p.u_only && (lora_units & 1);
+        const uint32_t u_col = second ? 0u : static_cast<uint32_t>(U_COL);
+        mbar_wait(second ? u_full2 : u_full, p.u_only ? ((lora_units >> 1) & 1) : (lora_units & 1));
         tc_fence_after();
         // the unit's rows are saved exactly once: by the range that owns its N-tile 0 (single-set calls only)
         const bool save = (p.u_out != nullptr) && (nt_first == 0) && (m0 + row < p.T);
@@ -407,14 +429,16 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
           const uint32_t u_row = smem_u32(u_tile) + s * V2_U_BYTES + row * 128;
           for (int j = 0; j < (p.r >> 4); ++j) {
             uint32_t v[16];
-            tmem_ld_32x16(tmem_base + lane_addr + U_COL + 64 * s + j * 16, v);
+            tmem_ld_32x16(tmem_base + lane_addr + u_col + 64 * s + j * 16, v);
             tmem_ld_wait();
             uint32_t pk[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i)
               pk[i] = pack_bf16x2(__uint_as_float(v[2 * i]) * p.scale, __uint_as_float(v[2 * i + 1]) * p.scale);
-            st_shared_v4(u_row + (((2 * j) ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
-            st_shared_v4(u_row + (((2 * j + 1) ^ sw) << 4), pk[4], pk[5], pk[6], pk[7]);
+            if (!p.u_only) {   // the smem operand tile is only needed when this kernel also runs the output tiles
+              st_shared_v4(u_row + (((2 * j) ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
+              st_shared_v4(u_row + (((2 * j + 1) ^ sw) << 4), pk[4], pk[5], pk[6], pk[7]);
+            }
             if (save && (s == 0 || p.u_ld > 0)) {   // u_ld layout: set s occupies columns [64 s, 64 s + r)
               uint4* ud = u_dst + (p.u_ld > 0 ? 8 * s : 0);
               ud[2 * j] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
@@ -425,7 +449,7 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
         tc_fence_before();
         asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy smem writes -> async proxy (peer-issued UMMA)
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(u_ready_leader);
+        if (lane == 0) mbar_arrive_cluster(second ? u_ready2_leader : u_ready_leader);
         ++lora_units;
       }
       if (LORA && p.u_only) {
