@@ -824,7 +824,15 @@ int attn_proj_fwd(const K1Args& a, cudaStream_t stream) {
   for (int s = 0; s < a.n_seg; ++s) al |= reinterpret_cast<uintptr_t>(a.y_seg[s]);
   if (al & 15) return fail(SAR_EINVAL, "attn_proj: pointers must be 16-byte aligned");
   int bn = a.block_n_override;
-  if (!bn) bn = (!lora && (a.d_out % 256 == 0 || (plain && a.d_out > 2048))) ? 256 : ((a.d_out % 192 == 0) ? 192 : 128);
+  if (!bn) {
+    bn = (!lora && (a.d_out % 256 == 0 || (plain && a.d_out > 2048))) ? 256 : ((a.d_out % 192 == 0) ? 192 : 128);
+    // Few rows (decode steps: one 256-row unit): the call is a weight-streaming problem, and with 256-wide tiles only
+    // d_out/256 pairs would pull the weights.  Narrow tiles put more SMs on the stream.
+    const long long units = static_cast<long long>(a.B) * ((a.T + 255) / 256);
+    const int n_seg = a.n_seg > 0 ? a.n_seg : 1;
+    const int pairs = device_info().num_sms / 2;
+    if (!lora && a.d_out % 128 == 0 && units * n_seg * ((a.d_out + bn - 1) / bn) < pairs) bn = 128;
+  }
   if (a.d_out % bn && !plain) return fail(SAR_EINVAL, "attn_proj: d_out not divisible by BLOCK_N");
   return k1v2_qv_lora_fwd(a, bn, stream);
 }

@@ -170,9 +170,19 @@ def _is_gelu(layer: nn.Module) -> bool:
         type(fn).__name__ == "GELUActivation" and not getattr(fn, "use_gelu_python", False)
 
 
+def _dropout_active(layer: nn.Module) -> bool:
+    """True when HF's body would apply dropout (training mode with a non-zero rate): the fused bodies have none."""
+    if not layer.training:
+        return False
+    attn_p = max(float(getattr(layer.self_attn, "dropout", 0.0)),
+                 float(getattr(getattr(layer, "encoder_attn", None), "dropout", 0.0) or 0.0))
+    return max(float(layer.dropout), float(layer.activation_dropout), attn_p) > 0.0
+
+
 def _fast_path_ok(layer: nn.Module, h: torch.Tensor, kwargs) -> bool:
     return (FUSED_BLOCKS_ENABLED and h.is_cuda and h.dtype == torch.bfloat16 and h.dim() == 3
-            and not torch.is_grad_enabled() and not kwargs.get("output_attentions", False))
+            and not torch.is_grad_enabled() and not kwargs.get("output_attentions", False)
+            and not _dropout_active(layer))
 
 
 def _ln(x: torch.Tensor, pack: _DensePack, eps: float) -> torch.Tensor:
