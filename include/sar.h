@@ -131,6 +131,17 @@ int sar_attn_proj_fwd_rows(const void* x, const void* W_cat, const void* bias_ca
                            int d_in, int d_out, int r, int n_adapters, float scale, uint32_t flags,
                            void* stream);
 
+/*
+ * Self-attention of one decode step over a static KV cache (head dim 64), position read from device memory:
+ *   cache_k[b,h,*pos,:] = k_new[b,h,:];  cache_v likewise;  out[b,h,:] = softmax_{t <= *pos}(q·cache_kᵀ)·cache_v
+ * q is already scaled (sar_attn_proj_fwd* folds head_dim^-0.5 into the projection).  Replaces DynamicCache.update +
+ * causal mask + SDPA of WhisperAttention.forward at tgt_len = 1 ($HF/models/whisper/modeling_whisper.py:326-350); a
+ * device-side position lets one captured CUDA graph serve every token.
+ *   q, k_new, v_new, out  bf16 [B, H, 64] (= [B, d] row-major);  cache_k, cache_v  bf16 [B, H, t_max, 64];  pos int64[1]
+ */
+int sar_decode_self_attn(const void* q, const void* k_new, const void* v_new, void* cache_k, void* cache_v,
+                         const int64_t* pos, void* out, int B, int H, int head_dim, int t_max, void* stream);
+
 /* epilogue activations of sar_linear_fwd */
 #define SAR_ACT_NONE 0
 #define SAR_ACT_GELU 1 /* erf-form GELU, HF ACT2FN["gelu"] */

@@ -231,6 +231,14 @@ int sar_dense_fwd(const void* x, int64_t ldx, int64_t x_batch_stride, const void
   return attn_proj_fwd(a, static_cast<cudaStream_t>(stream));
 }
 
+int sar_decode_self_attn(const void* q, const void* k_new, const void* v_new, void* cache_k, void* cache_v,
+                         const int64_t* pos, void* out, int B, int H, int head_dim, int t_max, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  return decode_self_attn(q, k_new, v_new, cache_k, cache_v, reinterpret_cast<const long long*>(pos), out, B, H,
+                          head_dim, t_max, static_cast<cudaStream_t>(stream));
+}
+
 int sar_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, int64_t M, int d, float eps,
                       void* stream) {
   int rc = require_sm100();

@@ -170,17 +170,15 @@ class StaticGreedyDecoder:
         dec = model.model.decoder
         B = st.tok.shape[0]
         h = dec.embed_tokens(st.tok).unsqueeze(1) + dec.embed_positions.weight.index_select(0, st.pos).unsqueeze(0)
-        mask = (st.arange <= st.pos).view(1, 1, 1, -1)
         idx = st.idx if st.use_idx else None
         for l, layer in enumerate(dec.layers):
             pk = layer._sar_pack
             qkv, cq = pk["self"].qkv.get(), pk["cross"].q.get()
             x = _ln(h, pk["ln1"], layer.self_attn_layer_norm.eps)
             q, k, v = qkv(x, idx if qkv.lora_mods else None)
-            st.K[l].index_copy_(2, st.pos, k)
-            st.V[l].index_copy_(2, st.pos, v)
-            o = F.scaled_dot_product_attention(q, st.K[l], st.V[l], attn_mask=mask, scale=1.0)
-            h = _dense(o, pk["self"].out, residual=h, head_major=True)
+            # cache write + masked softmax(q kᵀ) v in one launch, position read on the device
+            o = ops.decode_self_attn(q, k, v, st.K[l], st.V[l], st.pos)
+            h = _dense(o.view(B, 1, -1), pk["self"].out, residual=h)
             x = _ln(h, pk["ln2"], layer.encoder_attn_layer_norm.eps)
             (q,) = cq(x, idx if cq.lora_mods else None)
             o = F.scaled_dot_product_attention(q, st.CK[l], st.CV[l], scale=1.0)

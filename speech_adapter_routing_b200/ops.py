@@ -14,7 +14,7 @@ from ._lib import SAR_FLAG_SAVE_U, SAR_RPAD, check, lib
 
 
 # ---- instrumentation used by bench.py: kernel-launch counts and (optional) per-launch CUDA-event timing ----------
-LAUNCHES = {"k1": 0, "k2": 0, "k3": 0, "rows": 0, "proj": 0, "linear": 0, "ln": 0}   # kernels launched by libsar, by op (k2 = 2, k3 = 3, rows = 2)
+LAUNCHES = {"k1": 0, "k2": 0, "k3": 0, "rows": 0, "proj": 0, "linear": 0, "ln": 0, "attn": 0}   # kernels launched by libsar, by op (k2 = 2, k3 = 3, rows = 2)
 K1_TIMELINE = None   # set to a list to record (B*T, d_in, d_out, r, has_lora, start_event, end_event) per K1 call
 
 
@@ -260,6 +260,27 @@ def dense_fwd(x_base: torch.Tensor, ldx: int, x_batch_stride: int, W: torch.Tens
                                   int(y_batch_stride), B, T, d_in, d_out, int(act), flags, _stream(x_base)))
     _time_k1(K1_TIMELINE, "dense", B * T, d_in, d_out, 2.0 * B * T * d_in * d_out, launch)
     LAUNCHES["linear"] += 1
+
+
+def decode_self_attn(q: torch.Tensor, k_new: torch.Tensor, v_new: torch.Tensor, cache_k: torch.Tensor,
+                     cache_v: torch.Tensor, pos: torch.Tensor) -> torch.Tensor:
+    """One decode step of self-attention over the static cache (sar_decode_self_attn): writes k_new / v_new at ``pos``
+    (int64 device scalar) and returns softmax(q·Kᵀ)·V over positions 0..pos.  q / k_new / v_new: bf16 [B, H, 64] (any
+    contiguous view with B*H*64 elements); caches bf16 [B, H, Tmax, 64].  Returns bf16 [B, H*64]."""
+    _need_cuda(q, k_new, v_new, cache_k, cache_v, pos)
+    B, H, Tmax, hd = cache_k.shape
+    for t, name in ((q, "q"), (k_new, "k_new"), (v_new, "v_new")):
+        if t.dtype != torch.bfloat16 or not t.is_contiguous() or t.numel() != B * H * hd:
+            raise ValueError(f"{name} must be contiguous bf16 with B*H*64 elements")
+    if cache_k.dtype != torch.bfloat16 or not cache_k.is_contiguous() or not cache_v.is_contiguous():
+        raise ValueError("caches must be contiguous bf16 [B, H, Tmax, 64]")
+    if pos.dtype != torch.int64 or pos.numel() != 1:
+        raise ValueError("pos must be an int64 device scalar")
+    out = torch.empty(B, H * hd, dtype=torch.bfloat16, device=q.device)
+    check(lib().sar_decode_self_attn(_ptr(q), _ptr(k_new), _ptr(v_new), _ptr(cache_k), _ptr(cache_v), _ptr(pos),
+                                     _ptr(out), B, H, hd, Tmax, _stream(q)))
+    LAUNCHES["attn"] += 1
+    return out
 
 
 def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,

@@ -310,3 +310,25 @@ def test_attn_proj_large_v3_full_size(cuda_dev):
     u = ((x[b].float() @ A[k].float().t()) * 2.0).to(torch.bfloat16).float()
     ref = x[b].float() @ W[:d].float().t() + bias[:d].float() + (u @ Bp[k, :, :r].float().t() if k >= 0 else 0)
     assert rel_err(head_major_to_rows(split[0][b:b + 1])[0], ref) <= TIGHT
+
+
+# ------------------------------------------------------------------------------------------------ decode self-attention
+@pytest.mark.parametrize("B,H,Tmax,pos", [(3, 6, 64, 0), (64, 12, 128, 37), (5, 20, 448, 447), (2, 12, 256, 130)])
+def test_decode_self_attn_matches_sdpa(cuda_dev, B, H, Tmax, pos):
+    """sar_decode_self_attn vs an fp32 softmax(q kᵀ) v over positions 0..pos; the cache row at ``pos`` is written."""
+    g = torch.Generator().manual_seed(5)
+    dev = cuda_dev
+    K = torch.randn(B, H, Tmax, 64, generator=g).to(torch.bfloat16).to(dev)
+    V = torch.randn(B, H, Tmax, 64, generator=g).to(torch.bfloat16).to(dev)
+    q = (torch.randn(B, H, 64, generator=g) * 0.4).to(torch.bfloat16).to(dev)
+    kn = torch.randn(B, H, 64, generator=g).to(torch.bfloat16).to(dev)
+    vn = torch.randn(B, H, 64, generator=g).to(torch.bfloat16).to(dev)
+    K0, V0 = K.clone(), V.clone()
+    p = torch.tensor([pos], dtype=torch.long, device=dev)
+    out = ops.decode_self_attn(q, kn, vn, K, V, p)
+    K0[:, :, pos], V0[:, :, pos] = kn, vn
+    assert torch.equal(K, K0) and torch.equal(V, V0)          # exactly one cache row written, bit-exact
+    s = torch.einsum("bhd,bhtd->bht", q.float(), K0[:, :, :pos + 1].float())
+    ref = torch.einsum("bht,bhtd->bhd", torch.softmax(s, -1), V0[:, :, :pos + 1].float()).reshape(B, H * 64)
+    assert out.shape == (B, H * 64)
+    assert rel_err(out, ref) <= TIGHT
