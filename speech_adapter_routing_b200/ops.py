@@ -124,13 +124,14 @@ def attn_proj_fwd(x: torch.Tensor, W_cat: torch.Tensor, bias_cat: Optional[torch
                   A_cat: Optional[torch.Tensor], Bp_cat: Optional[torch.Tensor], utt_adapter: Optional[torch.Tensor],
                   seg_set: Sequence[int], seg_scale: Sequence[float], n_sets: int, scale: float,
                   x_head_major: bool = False, y_head_major: bool = True, block_n: int = 0,
-                  grid: int = 0, split: bool = True) -> List[torch.Tensor]:
+                  grid: int = 0, split: Optional[bool] = None) -> List[torch.Tensor]:
     """Fused attention projections (sar_attn_proj_fwd): up to three projections of the same x in one launch.
 
     x [B,T,d_in] (or [B,d_in/64,T,64] if ``x_head_major``); W_cat [n_seg*d_out, d_in]; A_cat [n_sets*n, r, d_in];
     Bp_cat [n_sets*n, d_out, 64].  Returns n_seg tensors, [B,d_out/64,T,64] if ``y_head_major`` else [B,T,d_out].
-    ``split`` (default): U = scale·x·A_kᵀ goes through a [B,T,64*n_sets] workspace and the projections run on the dense
-    256-wide kernel with one extra K block; ``split=False``: the single-launch kernel that keeps U in shared memory.
+    ``split=True``: U = scale·x·A_kᵀ goes through a [B,T,64*n_sets] workspace and the projections run on the dense
+    256-wide kernel with one extra K block; ``split=False``: the single-launch kernel that keeps U in shared memory;
+    ``None`` (default): split from SPLIT_MIN_ROWS rows up (bit-identical results either way).
     """
     _need_cuda(x, W_cat, bias_cat, A_cat, Bp_cat, utt_adapter)
     x = _bf16c(x, "x"); W_cat = _bf16c(W_cat, "W_cat"); bias_cat = _bf16c(bias_cat, "bias_cat")
@@ -166,7 +167,7 @@ def attn_proj_fwd(x: torch.Tensor, W_cat: torch.Tensor, bias_cat: Optional[torch
     flags = ((block_n & 0x3FF) << 8) | ((grid & 0x3FF) << 18)
     has_lora = n_adapters > 0
     ws = None
-    if has_lora and split and B * T >= SPLIT_MIN_ROWS:
+    if has_lora and (split if split is not None else B * T >= SPLIT_MIN_ROWS):
         ws = torch.empty(B * T * 64 * n_sets, dtype=torch.bfloat16, device=x.device)
 
     def launch():
