@@ -134,3 +134,39 @@ def test_block_oracle_reproduces_hf_encoder_layer_and_frontend():
         assert (y - y_hf).abs().max().item() <= 2.0 ** -7 * y_hf.abs().max().item()
         dec_h = torch.randn(2, 5, 128)
         assert torch.allclose(oblocks.lm_head(dec_h, model.proj_out.weight), model.proj_out(dec_h), atol=1e-5)
+
+
+def test_lora_oracle_agrees_with_an_independent_multi_lora_restatement():
+    """Second opinion for the UNPINNED LoRA oracle: vLLM's pure-torch multi-LoRA ops (vllm/lora/ops/torch_ops/lora_ops.py,
+    an independent restatement of PEFT's y = base + scaling * B(A(x)) with per-sequence adapter indices, installed in
+    this image) give the same result as oracle.lora.lora_linear_routed.  Not the reference itself — `peft` is not
+    installable here — so this does not lift the 'parity unpinned' status, it only guards the restatement."""
+    import importlib.util
+    from pathlib import Path
+
+    import pytest
+
+    try:
+        import vllm  # noqa: F401  (only to locate the file; the ops module itself imports nothing but torch)
+        path = Path(vllm.__file__).parent / "lora" / "ops" / "torch_ops" / "lora_ops.py"
+    except Exception:  # noqa: BLE001
+        pytest.skip("vllm not importable")
+    if not path.exists():
+        pytest.skip("vllm torch LoRA ops not present")
+    spec = importlib.util.spec_from_file_location("_vllm_lora_ops", path)
+    vops = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(vops)
+
+    c = fixtures.make_lora_case(5, 7, 64, 96, 8, 3, seed=4)
+    x, W, b = c.x.float(), c.W.float(), c.bias.float()
+    A, Bm, idx = c.A_stack.float(), c.B_stack.float(), c.utt_adapter.long()
+    want = olora.lora_linear_routed(x, W, b, A, Bm, c.scaling, c.utt_adapter)
+    Bsz, T, d_in = x.shape
+    flat = x.reshape(Bsz * T, d_in)
+    seq_len = torch.full((Bsz,), T, dtype=torch.long)
+    start = torch.arange(Bsz) * T
+    u = torch.zeros(Bsz * T, A.shape[1])
+    vops.sgmv_shrink(flat, A, u, start, seq_len, idx, Bsz, T, Bsz * T, c.scaling)
+    y = torch.nn.functional.linear(flat, W, b).clone()
+    vops.sgmv_expand(u, Bm, y, start, seq_len, idx, Bsz, T, Bsz * T, add_inputs=True)
+    assert torch.allclose(y.view(Bsz, T, -1), want, atol=1e-5, rtol=1e-5)
