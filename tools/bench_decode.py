@@ -22,7 +22,12 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--new", type=int, default=64)
     ap.add_argument("--skip-hf", action="store_true")
+    ap.add_argument("--model", default="whisper-small")
+    ap.add_argument("--adapters", type=int, default=4)
+    ap.add_argument("--rank", type=int, default=16)
     args = ap.parse_args()
+    if (args.model, args.adapters, args.rank) != ("whisper-small", 4, 16):
+        bench.configure(args.model, args.adapters, args.rank, args.batch)
     dev = torch.device("cuda", 0)
     router, cfg, clips, g = bench.build_b200_workload(dev, seed=1234)
     B = args.batch
