@@ -68,24 +68,6 @@ enum : int { EPI_RES = 1, EPI_GELU = 2, EPI_SCALE = 4 };
 // K loop (fc2, K = 3072) the epilogue is hidden anyway and the 8-warp variant is ~8 % slower, so the host picks by K.
 
 
-// erf-form GELU (HF ACT2FN["gelu"], what Whisper's fc1 uses): v * Phi(v), Phi(v) = 0.5 (1 + erf(v / sqrt 2)).
-// Evaluated through the identity Phi(v) = 1 / (1 + exp(-2 g(v))), g = atanh(erf(v / sqrt 2)), with g fitted by the odd
-// polynomial v (c0 + c1 v^2 + c2 v^4) on the clamped argument (minimax fit over [-8, 8], tools/fit_gelu.py):
-// max |error| of v * Phi(v) = 2.5e-5, i.e. below half a bf16 ulp of the output for |y| >= 0.0064.  Cost per element:
-// 6 fma-pipe instructions + MUFU.EX2 + MUFU.RCP; libdevice erff (or A&S 7.1.26: 13 fma-pipe instructions) made the
-// 4 epilogue warps pace the tensor pipe (ncu: 52 % tensor-active) because an SMSP issues one FFMA per 2 clk.
-__device__ __forceinline__ float gelu_erf(float v) {
-  constexpr float K = -2.0f * 1.4426950408889634f;   // exp(-2 g) = 2^(K g)
-  const float vc = fminf(fmaxf(v, -10.0f), 10.0f);   // keeps the fitted polynomial on its monotone branch
-  const float v2 = vc * vc;
-  float p = fmaf(v2, K * -0.0003515167885699055f, K * 0.037005646022542554f);
-  p = fmaf(p, v2, K * 0.7975078842850871f);
-  float e, r;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(vc * p));
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
-  return v * r;
-}
-
 template <int BLOCK_N, bool LORA>
 struct V2Smem {
   static constexpr int WH_BYTES = (BLOCK_N / 2) * 128;
@@ -823,6 +805,10 @@ int attn_proj_fwd(const K1Args& a, cudaStream_t stream) {
                  reinterpret_cast<uintptr_t>(a.bias);
   for (int s = 0; s < a.n_seg; ++s) al |= reinterpret_cast<uintptr_t>(a.y_seg[s]);
   if (al & 15) return fail(SAR_EINVAL, "attn_proj: pointers must be 16-byte aligned");
+  // <= 128 rows, dense, row-major: weight-streaming problem -> narrow single-CTA tiles on every SM (skinny_fwd.cu)
+  if (a.B == 1 && !a.block_n_override && !a.grid_override && !a.x_batch_stride && !a.y_batch_stride &&
+      skinny_applicable(a, a.T))
+    return skinny_fwd(a, a.T, stream);
   int bn = a.block_n_override;
   if (!bn) {
     bn = (!lora && (a.d_out % 256 == 0 || (plain && a.d_out > 2048))) ? 256 : ((a.d_out % 192 == 0) ? 192 : 128);

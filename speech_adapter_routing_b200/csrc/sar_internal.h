@@ -71,6 +71,8 @@ struct K1Args {
 int k1_qv_lora_fwd(const K1Args& a, cudaStream_t stream);
 int k1v2_qv_lora_fwd(const K1Args& a, int block_n, cudaStream_t stream);
 int attn_proj_fwd(const K1Args& a, cudaStream_t stream);
+bool skinny_applicable(const K1Args& a, int M);
+int skinny_fwd(const K1Args& a, int M, cudaStream_t stream);
 int attn_proj_fwd_rows(const K1Args& a, const int32_t* row_adapter, int M, cudaStream_t stream);
 int decode_self_attn(const void* q, const void* k_new, const void* v_new, void* cache_k, void* cache_v,
                      const long long* pos, void* out, int B, int H, int head_dim, int t_max, cudaStream_t stream);

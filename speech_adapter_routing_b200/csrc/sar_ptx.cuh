@@ -245,7 +245,30 @@ __device__ __forceinline__ void umma_commit_2sm(uint64_t* bar, uint16_t cta_mask
       : "memory");
 }
 
+// ----------------------------------------------------------------------------- programmatic dependent launch
+// Block until every prerequisite grid of this (programmatically serialised) launch has completed and its memory is
+// visible.  A no-op when the kernel was launched without the attribute.
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ----------------------------------------------------------------------------- misc
+// erf-form GELU (HF ACT2FN["gelu"], what Whisper's fc1 uses): v * Phi(v), Phi(v) = 0.5 (1 + erf(v / sqrt 2)).
+// Evaluated through the identity Phi(v) = 1 / (1 + exp(-2 g(v))), g = atanh(erf(v / sqrt 2)), with g fitted by the odd
+// polynomial v (c0 + c1 v^2 + c2 v^4) on the clamped argument (minimax fit over [-8, 8], tools/fit_gelu.py):
+// max |error| of v * Phi(v) = 2.5e-5, i.e. below half a bf16 ulp of the output for |y| >= 0.0064.  Cost per element:
+// 6 fma-pipe instructions + MUFU.EX2 + MUFU.RCP; libdevice erff (or A&S 7.1.26: 13 fma-pipe instructions) made the
+// 4 epilogue warps pace the tensor pipe (ncu: 52 % tensor-active) because an SMSP issues one FFMA per 2 clk.
+__device__ __forceinline__ float gelu_erf(float v) {
+  constexpr float K = -2.0f * 1.4426950408889634f;   // exp(-2 g) = 2^(K g)
+  const float vc = fminf(fmaxf(v, -10.0f), 10.0f);   // keeps the fitted polynomial on its monotone branch
+  const float v2 = vc * vc;
+  float p = fmaf(v2, K * -0.0003515167885699055f, K * 0.037005646022542554f);
+  p = fmaf(p, v2, K * 0.7975078842850871f);
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(vc * p));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return v * r;
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);  // .x = lo (low 16 bits), .y = hi
   return *reinterpret_cast<uint32_t*>(&h);

@@ -332,3 +332,32 @@ def test_decode_self_attn_matches_sdpa(cuda_dev, B, H, Tmax, pos):
     ref = torch.einsum("bht,bhtd->bhd", torch.softmax(s, -1), V0[:, :, :pos + 1].float()).reshape(B, H * 64)
     assert out.shape == (B, H * 64)
     assert rel_err(out, ref) <= TIGHT
+
+
+# ------------------------------------------------------------------------------------------------ skinny (<= 128 rows)
+@pytest.mark.parametrize("M,d_in,d_out,gelu,res", [
+    (64, 768, 3072, True, False),      # fc1 + GELU of a decode step, B = 64
+    (64, 3072, 768, False, True),      # fc2 + residual: 48 K blocks through a 10-stage ring
+    (64, 768, 768, False, True),       # out_proj + residual
+    (1, 768, 768, False, False),       # a single row
+    (100, 1280, 5120, True, False),    # large-v3 fc1, rows not a multiple of 32
+    (128, 1024, 1024, False, True),    # exactly one full tile of rows
+    (33, 384, 1536, True, False),      # tiny geometry
+])
+def test_skinny_dense_matches_oracle(cuda_dev, M, d_in, d_out, gelu, res):
+    """<= 128 rows route to the weight-streaming single-CTA kernel (skinny_fwd.cu): same contract as sar_linear_fwd."""
+    g = torch.Generator().manual_seed(13)
+    x = torch.randn(1, M, d_in, generator=g).to(torch.bfloat16)
+    W = (torch.randn(d_out, d_in, generator=g) * 0.02).to(torch.bfloat16)
+    b = (torch.randn(d_out, generator=g) * 0.02).to(torch.bfloat16)
+    r = torch.randn(1, M, d_out, generator=g).to(torch.bfloat16) if res else None
+    ref = oblocks.dense(x, W, b, r, gelu)
+    guard = torch.full((1, M + 2, d_out), 3.0, dtype=torch.bfloat16, device=cuda_dev)   # rows past M must stay untouched
+    y = ops.linear_fwd(x.to(cuda_dev), W.to(cuda_dev), b.to(cuda_dev), None if r is None else r.to(cuda_dev), int(gelu),
+                       out=guard[:, :M])
+    assert rel_err(y, ref) <= TIGHT
+    assert bool((guard[:, M:] == 3.0).all())
+    # identical to the CTA-pair kernel on the same operands up to one bf16 ulp of the largest value
+    y2 = ops.linear_fwd(x.to(cuda_dev), W.to(cuda_dev), b.to(cuda_dev), None if r is None else r.to(cuda_dev), int(gelu),
+                        block_n=128)
+    assert rel_err(y, y2.float()) <= 2.0 ** -8
