@@ -64,24 +64,13 @@ skinny_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
 
   if (warp == 4) {
     if (lane == 0) {
-      // Programmatic dependent launch: this grid may start while the previous kernel of the stream is still draining.
-      // The WEIGHT slices do not depend on it, so the first ring-full of them is requested immediately; everything
-      // that reads activations waits for the prerequisite grid first.
-      const int pre = KB < S ? KB : S;
-      for (int kb = 0; kb < pre; ++kb) {
-        mbar_arrive_expect_tx(&full[kb], STAGE_BYTES);
-        tma_load_2d(smem + kb * STAGE_BYTES + SK_X_BYTES, &tm_w, &full[kb], kb * SK_BLOCK_K, nt * BN);
-      }
-      grid_dependency_wait();
       for (int kb = 0; kb < KB; ++kb) {
         const int s = kb % S;
+        if (kb >= S) mbar_wait(&empty[s], ((kb / S) - 1) & 1);
         uint8_t* st = smem + s * STAGE_BYTES;
-        if (kb >= S) {
-          mbar_wait(&empty[s], ((kb / S) - 1) & 1);
-          mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
-          tma_load_2d(st + SK_X_BYTES, &tm_w, &full[s], kb * SK_BLOCK_K, nt * BN);
-        }
+        mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
         tma_load_2d(st, &tm_x, &full[s], kb * SK_BLOCK_K, 0);
+        tma_load_2d(st + SK_X_BYTES, &tm_w, &full[s], kb * SK_BLOCK_K, nt * BN);
       }
     }
   } else if (warp == 5) {
@@ -110,7 +99,6 @@ skinny_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
 #pragma unroll
     for (int j = 0; j < BN / 8; ++j)
       bb[j] = p.bias ? __ldg(reinterpret_cast<const uint4*>(p.bias + n0) + j) : make_uint4(0u, 0u, 0u, 0u);
-    grid_dependency_wait();   // the residual (and the buffer y may alias) belong to the previous kernel
 #pragma unroll
     for (int j = 0; j < BN / 8; ++j) {
       rr[j] = (p.residual && live)
@@ -201,17 +189,10 @@ static int skinny_launch(const K1Args& a, int M, cudaStream_t stream) {
     if (e != cudaSuccess) return fail_cuda(e, "skinny: cudaFuncSetAttribute");
     smem_set = dev.max_smem_optin;
   }
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(n_seg * p.nt_per_seg);
-  cfg.blockDim = dim3(SK_THREADS);
-  cfg.dynamicSmemBytes = smem_bytes;
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tm_x, tm_w, p);
+  // (A programmatic-dependent-launch variant that prefetched the weight slices before griddepcontrol.wait was measured:
+  // no gain — back-to-back grids fill every SM — and it would read stale weights if the preceding kernel wrote them.)
+  kern<<<n_seg * p.nt_per_seg, SK_THREADS, smem_bytes, stream>>>(tm_x, tm_w, p);
+  cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail_cuda(e, "skinny: launch");
   return SAR_OK;
 }
