@@ -132,6 +132,15 @@ int sar_attn_proj_fwd_rows(const void* x, const void* W_cat, const void* bias_ca
                            void* stream);
 
 /*
+ * softmax(Q·Kᵀ)·V for head dim 64 (flash-attention style forward on tcgen05 / TMEM / TMA), optional causal mask.
+ * Q is already scaled.  Replaces the attention_interface call of WhisperAttention.forward
+ * ($HF/models/whisper/modeling_whisper.py:341-350) on the head-major tensors sar_attn_proj_fwd writes.
+ *   q, out  bf16 [B, H, Tq, 64];  k, v  bf16 [B, H, Tk, 64];  causal needs Tq == Tk.
+ */
+int sar_attn_fwd(const void* q, const void* k, const void* v, void* out, int B, int H, int Tq, int Tk,
+                 int head_dim, int causal, void* stream);
+
+/*
  * Self-attention of one decode step over a static KV cache (head dim 64), position read from device memory:
  *   cache_k[b,h,*pos,:] = k_new[b,h,:];  cache_v likewise;  out[b,h,:] = softmax_{t <= *pos}(q·cache_kᵀ)·cache_v
  * q is already scaled (sar_attn_proj_fwd* folds head_dim^-0.5 into the projection).  Replaces DynamicCache.update +

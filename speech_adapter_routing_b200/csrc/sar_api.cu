@@ -231,6 +231,14 @@ int sar_dense_fwd(const void* x, int64_t ldx, int64_t x_batch_stride, const void
   return attn_proj_fwd(a, static_cast<cudaStream_t>(stream));
 }
 
+int sar_attn_fwd(const void* q, const void* k, const void* v, void* out, int B, int H, int Tq, int Tk, int head_dim,
+                 int causal, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  if (B <= 0 || H <= 0) return fail(SAR_EINVAL, "sar_attn_fwd: B and H must be positive");
+  return attn_fwd(q, k, v, out, B * H, Tq, Tk, head_dim, causal, static_cast<cudaStream_t>(stream));
+}
+
 int sar_decode_self_attn(const void* q, const void* k_new, const void* v_new, void* cache_k, void* cache_v,
                          const int64_t* pos, void* out, int B, int H, int head_dim, int t_max, void* stream) {
   int rc = require_sm100();

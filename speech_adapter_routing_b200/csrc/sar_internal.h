@@ -74,6 +74,8 @@ int attn_proj_fwd(const K1Args& a, cudaStream_t stream);
 bool skinny_applicable(const K1Args& a, int M);
 int skinny_fwd(const K1Args& a, int M, cudaStream_t stream);
 int attn_proj_fwd_rows(const K1Args& a, const int32_t* row_adapter, int M, cudaStream_t stream);
+int attn_fwd(const void* q, const void* k, const void* v, void* out, int BH, int Tq, int Tk, int head_dim, int causal,
+             cudaStream_t stream);
 int decode_self_attn(const void* q, const void* k_new, const void* v_new, void* cache_k, void* cache_v,
                      const long long* pos, void* out, int B, int H, int head_dim, int t_max, cudaStream_t stream);
 int layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, int64_t M, int d, float eps,

@@ -264,6 +264,20 @@ def dense_fwd(x_base: torch.Tensor, ldx: int, x_batch_stride: int, W: torch.Tens
     LAUNCHES["linear"] += 1
 
 
+def attn_fwd(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool = False) -> torch.Tensor:
+    """softmax(q·kᵀ)·v (sar_attn_fwd): q [B,H,Tq,64] (pre-scaled), k / v [B,H,Tk,64], bf16 contiguous -> [B,H,Tq,64]."""
+    _need_cuda(q, k, v)
+    q = _bf16c(q, "q"); k = _bf16c(k, "k"); v = _bf16c(v, "v")
+    B, H, Tq, hd = q.shape
+    Tk = k.shape[2]
+    if tuple(k.shape) != (B, H, Tk, hd) or tuple(v.shape) != (B, H, Tk, hd):
+        raise ValueError("k and v must be [B, H, Tk, 64]")
+    out = torch.empty_like(q)
+    check(lib().sar_attn_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(out), B, H, Tq, Tk, hd, int(causal), _stream(q)))
+    LAUNCHES["attn"] += 1
+    return out
+
+
 def decode_self_attn(q: torch.Tensor, k_new: torch.Tensor, v_new: torch.Tensor, cache_k: torch.Tensor,
                      cache_v: torch.Tensor, pos: torch.Tensor) -> torch.Tensor:
     """One decode step of self-attention over the static cache (sar_decode_self_attn): writes k_new / v_new at ``pos``

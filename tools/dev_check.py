@@ -410,6 +410,37 @@ def suite_blocks():
     return ok
 
 
+def suite_attn():
+    import torch.nn.functional as F
+    ok = True
+    g = torch.Generator().manual_seed(31)
+    for (B, H, Tq, Tk, causal) in [(1, 1, 128, 64, False), (2, 3, 128, 128, False), (2, 3, 200, 300, False),
+                                   (1, 2, 1500, 1500, False), (2, 2, 128, 1500, False), (2, 3, 128, 128, True),
+                                   (2, 2, 37, 37, True), (1, 2, 300, 300, True), (3, 2, 1, 77, False)]:
+        q = (torch.randn(B, H, Tq, 64, generator=g) * 0.35).to(torch.bfloat16).to(DEV)
+        k = torch.randn(B, H, Tk, 64, generator=g).to(torch.bfloat16).to(DEV)
+        v = torch.randn(B, H, Tk, 64, generator=g).to(torch.bfloat16).to(DEV)
+        ref = F.scaled_dot_product_attention(q.float(), k.float(), v.float(), is_causal=causal, scale=1.0)
+        out = ops.attn_fwd(q, k, v, causal)
+        torch.cuda.synchronize()
+        mx, rel, _ = err_stats(out, ref)
+        good = rel < 1e-2 and bool(torch.isfinite(out.float()).all())
+        ok &= good
+        log(f"[attn] B={B} H={H} Tq={Tq} Tk={Tk} causal={causal}: max_abs={mx:.4g} rel={rel:.3g} {'OK' if good else 'FAIL'}")
+    # perf at the bench shapes
+    for (B, H, Tq, Tk, causal, name) in [(64, 12, 1500, 1500, False, "encoder self"), (64, 12, 128, 1500, False, "decoder cross"),
+                                         (64, 12, 128, 128, True, "decoder self (causal)"), (64, 20, 1500, 1500, False, "large-v3 encoder")]:
+        q = (torch.randn(B, H, Tq, 64, device=DEV) * 0.35).to(torch.bfloat16)
+        k = torch.randn(B, H, Tk, 64, device=DEV, dtype=torch.bfloat16)
+        v = torch.randn(B, H, Tk, 64, device=DEV, dtype=torch.bfloat16)
+        fl = 4.0 * B * H * Tq * Tk * 64 * (0.5 if causal else 1.0)
+        ms = timeit(lambda: ops.attn_fwd(q, k, v, causal), iters=10)
+        ms2 = timeit(lambda: F.scaled_dot_product_attention(q, k, v, is_causal=causal, scale=1.0), iters=10)
+        log(f"[attn] perf {name}: libsar {ms*1e3:.1f} us ({fl/ms/1e9:.0f} TFLOP/s)   torch SDPA {ms2*1e3:.1f} us ({fl/ms2/1e9:.0f} TFLOP/s)")
+    log("[attn] suite", "PASSED" if ok else "FAILED")
+    return ok
+
+
 def timeit(fn, iters=20, warmup=3):
     for _ in range(warmup):
         fn()
