@@ -21,6 +21,7 @@ still RoutedLoRALinear (libsar K1/K3), so neither branch is a CPU or eager-LoRA 
 from __future__ import annotations
 
 import math
+import os
 import types
 from typing import Dict, List, Optional, Tuple
 
@@ -206,10 +207,19 @@ def _dense(x: torch.Tensor, pack: _DensePack, residual: Optional[torch.Tensor] =
     return y.view(B, T, -1)
 
 
+# Which softmax(q kᵀ) v runs where: libsar's tcgen05 flash-attention kernel (attn_fwd.cu) for up to OWN_ATTN_MAX_TQ query
+# rows per head — the decoder's self- and cross-attention, where it measured 86 us against 145 us for the library's
+# choice (an sm80 kernel) at 128 x 1500 — and torch SDPA (cuDNN's sm100 kernel, 540 us against our 811 us at
+# 1500 x 1500) above that.  SAR_OWN_ATTN_MAX_TQ=100000 puts every attention on libsar, =0 none.
+OWN_ATTN_MAX_TQ = int(os.environ.get("SAR_OWN_ATTN_MAX_TQ", "256"))
+
+
 def _sdpa(q, k, v, mask=None, causal=False):
     # q is pre-scaled inside the projection epilogue (HF applies `* self.scaling` to q_proj's output, then scale=1)
-    return F.scaled_dot_product_attention(q, k, v, attn_mask=mask, is_causal=causal and mask is None and q.shape[2] > 1,
-                                          scale=1.0)
+    causal = causal and mask is None and q.shape[2] > 1
+    if mask is None and q.shape[2] <= OWN_ATTN_MAX_TQ and (not causal or q.shape[2] == k.shape[2]):
+        return ops.attn_fwd(q, k, v, causal)
+    return F.scaled_dot_product_attention(q, k, v, attn_mask=mask, is_causal=causal, scale=1.0)
 
 
 # ------------------------------------------------------------------------------------------------ layer bodies

@@ -361,3 +361,25 @@ def test_skinny_dense_matches_oracle(cuda_dev, M, d_in, d_out, gelu, res):
     y2 = ops.linear_fwd(x.to(cuda_dev), W.to(cuda_dev), b.to(cuda_dev), None if r is None else r.to(cuda_dev), int(gelu),
                         block_n=128)
     assert rel_err(y, y2.float()) <= 2.0 ** -8
+
+
+# ------------------------------------------------------------------------------------------------ attention
+@pytest.mark.parametrize("B,H,Tq,Tk,causal", [
+    (1, 1, 128, 64, False), (2, 3, 200, 300, False), (1, 2, 1500, 1500, False), (2, 12, 128, 1500, False),
+    (2, 3, 128, 128, True), (2, 2, 37, 37, True), (1, 2, 300, 300, True), (3, 2, 1, 77, False), (1, 20, 448, 448, True),
+])
+def test_attn_fwd_matches_fp32_softmax(cuda_dev, B, H, Tq, Tk, causal):
+    """sar_attn_fwd (tcgen05 flash-attention forward, head dim 64) vs fp32 softmax(q kᵀ) v on the same bf16 inputs:
+    ragged last key tile, query tiles past Tq, causal diagonal, one-row queries.  Tolerance: P is rounded to bf16 before
+    the PV product (like every flash-attention kernel): 2^-7 of max|ref|."""
+    g = torch.Generator().manual_seed(31)
+    q = (torch.randn(B, H, Tq, 64, generator=g) * 0.35).to(torch.bfloat16).to(cuda_dev)
+    k = torch.randn(B, H, Tk, 64, generator=g).to(torch.bfloat16).to(cuda_dev)
+    v = torch.randn(B, H, Tk, 64, generator=g).to(torch.bfloat16).to(cuda_dev)
+    ref = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float(), is_causal=causal, scale=1.0)
+    out = ops.attn_fwd(q, k, v, causal)
+    assert out.shape == q.shape and out.dtype == torch.bfloat16
+    assert rel_err(out, ref) <= TIGHT
+    # a (b, h) pair computed alone gives identical bits (tiles never cross heads)
+    one = ops.attn_fwd(q[:1, :1].contiguous(), k[:1, :1].contiguous(), v[:1, :1].contiguous(), causal)
+    assert torch.equal(one[0, 0], out[0, 0])
