@@ -376,7 +376,7 @@ def run_b200_arm(args):
                        "parallelism": f"utterance-sharded x{world}, adapters replicated, no data-path collective",
                        "l2": "inputs rotate over 3 buffers; each activation tensor (147 MB) exceeds the 126 MB L2",
                        "weights": "random-init",
-                       "rest_of_model": "SDPA = torch/cuDNN, conv front-end / embeddings / lm_head = torch (library code)"},
+                       "rest_of_model": "libsar kernels for every projection / FFN / LayerNorm / conv front-end / lm head and the decoder's attention; encoder 1500x1500 softmax(QK^T)V = torch SDPA (cuDNN); embedding gathers = torch"},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
