@@ -151,6 +151,17 @@ int sar_attn_fwd(const void* q, const void* k, const void* v, void* out, int B, 
 int sar_decode_self_attn(const void* q, const void* k_new, const void* v_new, void* cache_k, void* cache_v,
                          const int64_t* pos, void* out, int B, int H, int head_dim, int t_max, void* stream);
 
+/*
+ * Cross-attention of one decode step (one query token per utterance, head dim 64) over read-only encoder K / V:
+ *   out[b,h,:] = softmax_t( q[b,h,:]·k[b,h,t,:] ) · v[b,h,t,:],  t < Tk            (q is pre-scaled)
+ * Replaces the attention_interface call of WhisperAttention.forward for encoder_attn at tgt_len = 1
+ * ($HF/models/whisper/modeling_whisper.py:341-350) inside the per-sample decode loop of
+ * src/models/adapter_router.py:744-750.  HBM-bound: streams 2·Tk·128 B per (b, h) per token.
+ *   q, out  bf16 [B, H, 64];  k, v  bf16 [B, H, Tk, 64]
+ */
+int sar_decode_cross_attn(const void* q, const void* k, const void* v, void* out, int B, int H, int head_dim, int Tk,
+                          void* stream);
+
 /* epilogue activations of sar_linear_fwd */
 #define SAR_ACT_NONE 0
 #define SAR_ACT_GELU 1 /* erf-form GELU, HF ACT2FN["gelu"] */

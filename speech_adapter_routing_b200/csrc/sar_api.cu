@@ -247,6 +247,13 @@ int sar_decode_self_attn(const void* q, const void* k_new, const void* v_new, vo
                           head_dim, t_max, static_cast<cudaStream_t>(stream));
 }
 
+int sar_decode_cross_attn(const void* q, const void* k, const void* v, void* out, int B, int H, int head_dim, int Tk,
+                          void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  return decode_cross_attn(q, k, v, out, B, H, head_dim, Tk, static_cast<cudaStream_t>(stream));
+}
+
 int sar_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, int64_t M, int d, float eps,
                       void* stream) {
   int rc = require_sm100();

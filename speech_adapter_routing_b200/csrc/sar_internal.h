@@ -78,6 +78,8 @@ int attn_fwd(const void* q, const void* k, const void* v, void* out, int BH, int
              cudaStream_t stream);
 int decode_self_attn(const void* q, const void* k_new, const void* v_new, void* cache_k, void* cache_v,
                      const long long* pos, void* out, int B, int H, int head_dim, int t_max, cudaStream_t stream);
+int decode_cross_attn(const void* q, const void* k, const void* v, void* out, int B, int H, int head_dim, int Tk,
+                      cudaStream_t stream);
 int layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, int64_t M, int d, float eps,
                   cudaStream_t stream);
 

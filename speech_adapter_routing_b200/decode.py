@@ -21,7 +21,6 @@ from __future__ import annotations
 from typing import Dict, List, NamedTuple, Optional, Sequence
 
 import torch
-import torch.nn.functional as F
 
 from . import ops
 from ._lib import SAR_ACT_GELU
@@ -181,8 +180,8 @@ class StaticGreedyDecoder:
             h = _dense(o.view(B, 1, -1), pk["self"].out, residual=h)
             x = _ln(h, pk["ln2"], layer.encoder_attn_layer_norm.eps)
             (q,) = cq(x, idx if cq.lora_mods else None)
-            o = F.scaled_dot_product_attention(q, st.CK[l], st.CV[l], scale=1.0)
-            h = _dense(o, pk["cross"].out, residual=h, head_major=True, inplace=True)
+            o = ops.decode_cross_attn(q, st.CK[l], st.CV[l])      # streams the encoder K / V of every (b, h) once
+            h = _dense(o.view(B, 1, -1), pk["cross"].out, residual=h, inplace=True)
             x = _ln(h, pk["ln3"], layer.final_layer_norm.eps)
             f = _dense(x, pk["fc1"], act=SAR_ACT_GELU)
             h = _dense(f, pk["fc2"], residual=h, inplace=True)

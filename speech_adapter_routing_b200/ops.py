@@ -299,6 +299,22 @@ def decode_self_attn(q: torch.Tensor, k_new: torch.Tensor, v_new: torch.Tensor, 
     return out
 
 
+def decode_cross_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor) -> torch.Tensor:
+    """Cross-attention of one decode step (sar_decode_cross_attn): q bf16 with B*H*64 elements (pre-scaled), k / v bf16
+    [B, H, Tk, 64] contiguous.  Returns bf16 [B, H*64]."""
+    _need_cuda(q, k, v)
+    B, H, Tk, hd = k.shape
+    if q.dtype != torch.bfloat16 or not q.is_contiguous() or q.numel() != B * H * hd:
+        raise ValueError("q must be contiguous bf16 with B*H*64 elements")
+    for t, name in ((k, "k"), (v, "v")):
+        if t.dtype != torch.bfloat16 or not t.is_contiguous() or t.shape != k.shape:
+            raise ValueError(f"{name} must be contiguous bf16 [B, H, Tk, 64]")
+    out = torch.empty(B, H * hd, dtype=torch.bfloat16, device=q.device)
+    check(lib().sar_decode_cross_attn(_ptr(q), _ptr(k), _ptr(v), _ptr(out), B, H, hd, Tk, _stream(q)))
+    LAUNCHES["attn"] += 1
+    return out
+
+
 def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float = 1e-5,
                   out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """LayerNorm over the last dim (sar_layernorm_fwd): bf16 in/out, fp32 statistics."""

@@ -334,6 +334,26 @@ def test_decode_self_attn_matches_sdpa(cuda_dev, B, H, Tmax, pos):
     assert rel_err(out, ref) <= TIGHT
 
 
+@pytest.mark.parametrize("B,H,Tk", [(3, 6, 1), (64, 12, 1500), (5, 20, 1500), (2, 12, 77), (1, 8, 4096)])
+def test_decode_cross_attn_matches_fp32_softmax(cuda_dev, B, H, Tk):
+    """sar_decode_cross_attn (one query token per utterance over read-only encoder K / V) vs an fp32 softmax(q kᵀ) v;
+    K / V must come back untouched."""
+    g = torch.Generator().manual_seed(6)
+    dev = cuda_dev
+    K = torch.randn(B, H, Tk, 64, generator=g).to(torch.bfloat16).to(dev)
+    V = torch.randn(B, H, Tk, 64, generator=g).to(torch.bfloat16).to(dev)
+    q = (torch.randn(B, H, 1, 64, generator=g) * 0.4).to(torch.bfloat16).to(dev)
+    K0, V0 = K.clone(), V.clone()
+    out = ops.decode_cross_attn(q, K, V)
+    assert torch.equal(K, K0) and torch.equal(V, V0)
+    s = torch.einsum("bhd,bhtd->bht", q[:, :, 0].float(), K.float())
+    ref = torch.einsum("bht,bhtd->bhd", torch.softmax(s, -1), V.float()).reshape(B, H * 64)
+    assert out.shape == (B, H * 64)
+    assert rel_err(out, ref) <= TIGHT
+    out2 = ops.decode_cross_attn(q, K, V)
+    assert torch.equal(out, out2)                                # fixed-order reduction: deterministic
+
+
 # ------------------------------------------------------------------------------------------------ skinny (<= 128 rows)
 @pytest.mark.parametrize("M,d_in,d_out,gelu,res", [
     (64, 768, 3072, True, False),      # fc1 + GELU of a decode step, B = 64
