@@ -513,12 +513,17 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int e = 8 * j + 2 * i;
-              float a0 = __uint_as_float(e < 32 ? v0[e & 31] : v1[e & 31]) + __uint_as_float(bw[i] << 16);
-              float a1 = __uint_as_float(e < 32 ? v0[(e + 1) & 31] : v1[(e + 1) & 31]) +
-                         __uint_as_float(bw[i] & 0xFFFF0000u);
-              if constexpr ((EPI & EPI_GELU) != 0) {
-                a0 = gelu_erf(a0);
-                a1 = gelu_erf(a1);
+              float a0, a1;
+              if constexpr ((EPI & EPI_GELU) != 0) {   // bias add and activation on the packed fp32 pipe
+                const float2 ge = gelu_erf2(fadd2(
+                    make_float2(__uint_as_float(e < 32 ? v0[e & 31] : v1[e & 31]),
+                                __uint_as_float(e < 32 ? v0[(e + 1) & 31] : v1[(e + 1) & 31])),
+                    make_float2(__uint_as_float(bw[i] << 16), __uint_as_float(bw[i] & 0xFFFF0000u))));
+                a0 = ge.x;
+                a1 = ge.y;
+              } else {
+                a0 = __uint_as_float(e < 32 ? v0[e & 31] : v1[e & 31]) + __uint_as_float(bw[i] << 16);
+                a1 = __uint_as_float(e < 32 ? v0[(e + 1) & 31] : v1[(e + 1) & 31]) + __uint_as_float(bw[i] & 0xFFFF0000u);
               }
               if constexpr ((EPI & EPI_SCALE) != 0) {
                 a0 *= oscale;

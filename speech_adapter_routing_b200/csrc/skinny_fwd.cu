@@ -125,8 +125,9 @@ skinny_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ 
             float a0 = __uint_as_float(v[8 * j + 2 * i]) + __uint_as_float(bw[i] << 16);
             float a1 = __uint_as_float(v[8 * j + 2 * i + 1]) + __uint_as_float(bw[i] & 0xFFFF0000u);
             if (p.act == SAR_ACT_GELU) {
-              a0 = gelu_erf(a0);
-              a1 = gelu_erf(a1);
+              const float2 ge = gelu_erf2(make_float2(a0, a1));
+              a0 = ge.x;
+              a1 = ge.y;
             }
             a0 += __uint_as_float(rw[i] << 16);
             a1 += __uint_as_float(rw[i] & 0xFFFF0000u);
