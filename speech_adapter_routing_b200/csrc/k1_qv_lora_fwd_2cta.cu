@@ -513,26 +513,15 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
               const int e = 8 * j + 2 * i;
-              float a0, a1;
-              if constexpr ((EPI & EPI_GELU) != 0) {   // bias add and activation on the packed fp32 pipe
-                const float2 ge = gelu_erf2(fadd2(
-                    make_float2(__uint_as_float(e < 32 ? v0[e & 31] : v1[e & 31]),
-                                __uint_as_float(e < 32 ? v0[(e + 1) & 31] : v1[(e + 1) & 31])),
-                    make_float2(__uint_as_float(bw[i] << 16), __uint_as_float(bw[i] & 0xFFFF0000u))));
-                a0 = ge.x;
-                a1 = ge.y;
-              } else {
-                a0 = __uint_as_float(e < 32 ? v0[e & 31] : v1[e & 31]) + __uint_as_float(bw[i] << 16);
-                a1 = __uint_as_float(e < 32 ? v0[(e + 1) & 31] : v1[(e + 1) & 31]) + __uint_as_float(bw[i] & 0xFFFF0000u);
-              }
-              if constexpr ((EPI & EPI_SCALE) != 0) {
-                a0 *= oscale;
-                a1 *= oscale;
-              }
-              if constexpr ((EPI & EPI_RES) != 0) {
-                a0 += __uint_as_float(rw[i] << 16);
-                a1 += __uint_as_float(rw[i] & 0xFFFF0000u);
-              }
+              // bias add, activation, scale and residual add on the packed fp32 pipe (the epilogue is issue-bound)
+              float2 av = fadd2(make_float2(__uint_as_float(e < 32 ? v0[e & 31] : v1[e & 31]),
+                                            __uint_as_float(e < 32 ? v0[(e + 1) & 31] : v1[(e + 1) & 31])),
+                                make_float2(__uint_as_float(bw[i] << 16), __uint_as_float(bw[i] & 0xFFFF0000u)));
+              if constexpr ((EPI & EPI_GELU) != 0) av = gelu_erf2(av);
+              if constexpr ((EPI & EPI_SCALE) != 0) av = fmul2(av, make_float2(oscale, oscale));
+              if constexpr ((EPI & EPI_RES) != 0)
+                av = fadd2(av, make_float2(__uint_as_float(rw[i] << 16), __uint_as_float(rw[i] & 0xFFFF0000u)));
+              const float a0 = av.x, a1 = av.y;
               pk[i] = pack_bf16x2(a0, a1);
             }
             st_shared_v4(saddr, pk[0], pk[1], pk[2], pk[3]);
