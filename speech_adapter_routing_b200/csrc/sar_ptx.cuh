@@ -312,7 +312,7 @@ __device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepco
 // polynomial v (c0 + c1 v^2 + c2 v^4) on the clamped argument (minimax fit over [-8, 8], tools/fit_gelu.py):
 // max |error| of v * Phi(v) = 2.5e-5, i.e. below half a bf16 ulp of the output for |y| >= 0.0064.  Cost per element:
 // 6 fma-pipe instructions + MUFU.EX2 + MUFU.RCP; libdevice erff (or A&S 7.1.26: 13 fma-pipe instructions) made the
-// 4 epilogue warps pace the tensor pipe (ncu: 52 % tensor-active) because an SMSP issues one FFMA per 2 clk.
+// 4 epilogue warps pace the tensor pipe (ncu: 52 % tensor-active): the epilogue is bound by issue slots.
 __device__ __forceinline__ float gelu_erf(float v) {
   constexpr float K = -2.0f * 1.4426950408889634f;   // exp(-2 g) = 2^(K g)
   const float vc = fminf(fmaxf(v, -10.0f), 10.0f);   // keeps the fitted polynomial on its monotone branch

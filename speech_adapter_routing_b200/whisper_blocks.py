@@ -208,8 +208,8 @@ def _dense(x: torch.Tensor, pack: _DensePack, residual: Optional[torch.Tensor] =
 
 
 # Which softmax(q kᵀ) v runs where: libsar's tcgen05 flash-attention kernel (attn_fwd.cu) for up to OWN_ATTN_MAX_TQ query
-# rows per head — the decoder's self- and cross-attention, where it measured 86 us against 145 us for the library's
-# choice (an sm80 kernel) at 128 x 1500 — and torch SDPA (cuDNN's sm100 kernel, 540 us against our 811 us at
+# rows per head — the decoder's self- and cross-attention, where it measured 84 us against 145 us for the library's
+# choice (an sm80 kernel) at 128 x 1500 — and torch SDPA (cuDNN's sm100 kernel, 540 us against our 762 us at
 # 1500 x 1500) above that.  SAR_OWN_ATTN_MAX_TQ=100000 puts every attention on libsar, =0 none.
 OWN_ATTN_MAX_TQ = int(os.environ.get("SAR_OWN_ATTN_MAX_TQ", "256"))
 

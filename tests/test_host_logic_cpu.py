@@ -199,3 +199,26 @@ def test_whisper_lora_wrapper_api_offline(monkeypatch):
     assert w2.lora_config.r == 4
     assert sar.get_model_name("whisper-large") == "openai/whisper-large-v3"
     assert sar.get_model_info("whisper-small")["hidden_size"] == 768
+
+
+def test_attention_dispatch_picks_the_own_kernel_for_decoder_shapes_only(monkeypatch):
+    """whisper_blocks._sdpa: libsar's attention kernel up to OWN_ATTN_MAX_TQ query rows and only without an explicit mask
+    (causal only when square); everything else — the 1500 x 1500 encoder attention — goes to torch SDPA."""
+    from speech_adapter_routing_b200 import ops, whisper_blocks as wb
+
+    calls = []
+    monkeypatch.setattr(ops, "attn_fwd", lambda q, k, v, causal: calls.append(("own", bool(causal))) or q)
+    monkeypatch.setattr(wb.F, "scaled_dot_product_attention",
+                        lambda q, k, v, attn_mask=None, is_causal=False, scale=None: calls.append(("torch", bool(is_causal))) or q)
+    monkeypatch.setattr(wb, "OWN_ATTN_MAX_TQ", 256)
+    t = lambda tq: torch.zeros(1, 2, tq, 64)
+    wb._sdpa(t(128), t(1500), t(1500))                              # decoder cross-attention
+    wb._sdpa(t(128), t(128), t(128), causal=True)                   # decoder self-attention
+    wb._sdpa(t(1), t(77), t(77), causal=True)                       # one query row: the causal mask is a no-op
+    wb._sdpa(t(1500), t(1500), t(1500))                             # encoder self-attention
+    wb._sdpa(t(128), t(128), t(128), mask=torch.zeros(1, 1, 128, 128), causal=True)   # explicit mask
+    assert calls == [("own", False), ("own", True), ("own", False), ("torch", False), ("torch", False)]
+    monkeypatch.setattr(wb, "OWN_ATTN_MAX_TQ", 0)
+    calls.clear()
+    wb._sdpa(t(128), t(1500), t(1500))
+    assert calls == [("torch", False)]
