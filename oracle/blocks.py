@@ -53,6 +53,23 @@ def attn_projections(x: torch.Tensor, Ws: Sequence[torch.Tensor], biases: Sequen
     return outs
 
 
+def attention(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor, causal: bool = False,
+              n_keys: Optional[int] = None) -> torch.Tensor:
+    """softmax(q kᵀ) v per head — eager_attention_forward (:215-238) with scaling = 1 (the query is already scaled by
+    the projection) and HF's additive causal mask written as an explicit ``key <= query`` rule; ``n_keys`` limits the
+    keys to the first n (a static decode cache attended up to the current position).  q [B, h, Tq, dh], k / v
+    [B, h, Tk, dh], fp32 arithmetic; returns the head-major [B, h, Tq, dh] (HF transposes it back before out_proj)."""
+    q, k, v = q.float(), k.float(), v.float()
+    if n_keys is not None:
+        k, v = k[:, :, :n_keys], v[:, :, :n_keys]
+    w = torch.matmul(q, k.transpose(2, 3))
+    if causal:
+        Tq, Tk = q.shape[2], k.shape[2]
+        allowed = torch.arange(Tk)[None, :] <= (torch.arange(Tq)[:, None] + (Tk - Tq))
+        w = w.masked_fill(~allowed, float("-inf"))
+    return torch.matmul(torch.softmax(w, dim=-1), v)
+
+
 def conv_frontend(x: torch.Tensor, w1: torch.Tensor, b1: torch.Tensor, w2: torch.Tensor, b2: torch.Tensor,
                   pos: torch.Tensor, round_mid_to_bf16: bool = True) -> torch.Tensor:
     """gelu(conv1) -> gelu(conv2) -> permute -> + embed_positions (:626-633).  ``round_mid_to_bf16`` rounds conv1's

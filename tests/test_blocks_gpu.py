@@ -328,8 +328,7 @@ def test_decode_self_attn_matches_sdpa(cuda_dev, B, H, Tmax, pos):
     out = ops.decode_self_attn(q, kn, vn, K, V, p)
     K0[:, :, pos], V0[:, :, pos] = kn, vn
     assert torch.equal(K, K0) and torch.equal(V, V0)          # exactly one cache row written, bit-exact
-    s = torch.einsum("bhd,bhtd->bht", q.float(), K0[:, :, :pos + 1].float())
-    ref = torch.einsum("bht,bhtd->bhd", torch.softmax(s, -1), V0[:, :, :pos + 1].float()).reshape(B, H * 64)
+    ref = oblocks.attention(q.cpu()[:, :, None], K0.cpu(), V0.cpu(), n_keys=pos + 1).reshape(B, H * 64)
     assert out.shape == (B, H * 64)
     assert rel_err(out, ref) <= TIGHT
 
@@ -346,8 +345,7 @@ def test_decode_cross_attn_matches_fp32_softmax(cuda_dev, B, H, Tk):
     K0, V0 = K.clone(), V.clone()
     out = ops.decode_cross_attn(q, K, V)
     assert torch.equal(K, K0) and torch.equal(V, V0)
-    s = torch.einsum("bhd,bhtd->bht", q[:, :, 0].float(), K.float())
-    ref = torch.einsum("bht,bhtd->bhd", torch.softmax(s, -1), V.float()).reshape(B, H * 64)
+    ref = oblocks.attention(q.cpu(), K.cpu(), V.cpu()).reshape(B, H * 64)
     assert out.shape == (B, H * 64)
     assert rel_err(out, ref) <= TIGHT
     out2 = ops.decode_cross_attn(q, K, V)
@@ -396,7 +394,7 @@ def test_attn_fwd_matches_fp32_softmax(cuda_dev, B, H, Tq, Tk, causal):
     q = (torch.randn(B, H, Tq, 64, generator=g) * 0.35).to(torch.bfloat16).to(cuda_dev)
     k = torch.randn(B, H, Tk, 64, generator=g).to(torch.bfloat16).to(cuda_dev)
     v = torch.randn(B, H, Tk, 64, generator=g).to(torch.bfloat16).to(cuda_dev)
-    ref = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float(), is_causal=causal, scale=1.0)
+    ref = oblocks.attention(q.cpu(), k.cpu(), v.cpu(), causal=causal)   # oracle pinned against HF's eager attention
     out = ops.attn_fwd(q, k, v, causal)
     assert out.shape == q.shape and out.dtype == torch.bfloat16
     assert rel_err(out, ref) <= TIGHT

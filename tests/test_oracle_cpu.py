@@ -125,7 +125,7 @@ def test_block_oracle_reproduces_hf_encoder_layer_and_frontend():
         q, k, v = oblocks.attn_projections(xn, [a.q_proj.weight, a.k_proj.weight, a.v_proj.weight],
                                            [a.q_proj.bias, None, a.v_proj.bias], [None, None, None], 2.0, none,
                                            [a.scaling, 1.0, 1.0], a.num_heads)
-        o = F.scaled_dot_product_attention(q, k, v, scale=1.0).transpose(1, 2).reshape(2, 1500, -1)
+        o = oblocks.attention(q, k, v).transpose(1, 2).reshape(2, 1500, -1)
         h1 = oblocks.dense(o, a.out_proj.weight, a.out_proj.bias, residual=h)
         xn = oblocks.layer_norm(h1, layer.final_layer_norm.weight, layer.final_layer_norm.bias)
         f = oblocks.dense(xn, layer.fc1.weight, layer.fc1.bias, gelu=True)
@@ -134,6 +134,33 @@ def test_block_oracle_reproduces_hf_encoder_layer_and_frontend():
         assert (y - y_hf).abs().max().item() <= 2.0 ** -7 * y_hf.abs().max().item()
         dec_h = torch.randn(2, 5, 128)
         assert torch.allclose(oblocks.lm_head(dec_h, model.proj_out.weight), model.proj_out(dec_h), atol=1e-5)
+
+
+def test_attention_oracle_reproduces_hf_eager_attention_with_and_without_the_causal_mask():
+    """oracle.blocks.attention vs HF's own eager_attention_forward ($HF/models/whisper/modeling_whisper.py:215-238) fed
+    with the additive causal mask HF builds for the decoder (0 on and below the diagonal, dtype-min above), and vs a
+    per-position loop for the static-cache decode form (keys 0..pos)."""
+    from transformers.models.whisper.modeling_whisper import eager_attention_forward
+
+    from oracle import blocks as oblocks
+
+    g = torch.Generator().manual_seed(11)
+    B, H, T, S, dh = 2, 3, 37, 50, 64
+    q = torch.randn(B, H, T, dh, generator=g) * 0.3
+    k = torch.randn(B, H, S, dh, generator=g)
+    v = torch.randn(B, H, S, dh, generator=g)
+    mod = torch.nn.Module().eval()
+    hf, _ = eager_attention_forward(mod, q, k, v, None, scaling=1.0)
+    assert torch.allclose(oblocks.attention(q, k, v), hf.transpose(1, 2), atol=1e-6)
+    ks, vs = k[:, :, :T], v[:, :, :T]
+    mask = torch.full((T, T), torch.finfo(torch.float32).min).triu(1)[None, None]
+    hf_c, _ = eager_attention_forward(mod, q, ks, vs, mask, scaling=1.0)
+    assert torch.allclose(oblocks.attention(q, ks, vs, causal=True), hf_c.transpose(1, 2), atol=1e-6)
+    # decode form: one query row at position pos over a cache of S slots = row pos of the causal result
+    pos = 20
+    one = oblocks.attention(q[:, :, pos:pos + 1], k, v, n_keys=pos + 1)
+    full = oblocks.attention(q[:, :, :pos + 1], k[:, :, :pos + 1], v[:, :, :pos + 1], causal=True)
+    assert torch.allclose(one[:, :, 0], full[:, :, pos], atol=1e-6)
 
 
 def test_lora_oracle_agrees_with_an_independent_multi_lora_restatement():
