@@ -20,8 +20,21 @@ def test_header_declares_the_documented_entry_points():
     fns = declared_functions()
     for name in ["sar_version", "sar_last_error", "sar_device_ok", "sar_workspace_bytes", "sar_qv_lora_fwd",
                  "sar_qv_lora_fwd_rows", "sar_router_fwd", "sar_qv_lora_bwd", "sar_qv_lora_fwd_pair",
-                 "sar_attn_proj_fwd", "sar_linear_fwd", "sar_dense_fwd", "sar_layernorm_fwd"]:
+                 "sar_attn_proj_fwd", "sar_attn_proj_fwd_rows", "sar_linear_fwd", "sar_dense_fwd", "sar_layernorm_fwd",
+                 "sar_attn_fwd", "sar_decode_self_attn", "sar_decode_cross_attn"]:
         assert name in fns
+
+
+def test_ctypes_bindings_have_the_arity_the_header_declares():
+    """Every prototype in include/sar.h has as many parameters as the ctypes argtypes bound in _lib.py (a drifted
+    binding would otherwise corrupt the call silently)."""
+    text = re.sub(r"/\*.*?\*/", "", HEADER.read_text(), flags=re.S)
+    protos = dict(re.findall(r"\b(sar_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", text))
+    assert set(protos) == set(_lib._SIGNATURES)
+    for name, params in protos.items():
+        params = params.strip()
+        n = 0 if params in ("", "void") else len(params.split(","))
+        assert n == len(_lib._SIGNATURES[name][1]), f"{name}: header has {n} parameters, ctypes binds {len(_lib._SIGNATURES[name][1])}"
 
 
 def test_library_exports_every_declared_symbol(libsar):
