@@ -207,18 +207,24 @@ def _dense(x: torch.Tensor, pack: _DensePack, residual: Optional[torch.Tensor] =
     return y.view(B, T, -1)
 
 
-# Which softmax(q kᵀ) v runs where: libsar's tcgen05 flash-attention kernel (attn_fwd.cu) for up to OWN_ATTN_MAX_TQ query
-# rows per head — the decoder's self- and cross-attention, where it measured 84 us against 145 us for the library's
-# choice (an sm80 kernel) at 128 x 1500 — and torch SDPA (cuDNN's sm100 kernel, 540 us against our 762 us at
-# 1500 x 1500) above that.  SAR_OWN_ATTN_MAX_TQ=100000 puts every attention on libsar, =0 none.
-OWN_ATTN_MAX_TQ = int(os.environ.get("SAR_OWN_ATTN_MAX_TQ", "256"))
+# Which softmax(q kᵀ) v runs where (B = 64, h = 12, measured on B200, libsar's attn_fwd.cu vs torch SDPA):
+#   cross-attention  128 x 1500:  84 us vs 145 us (the library picks an sm80 kernel there)   -> libsar
+#   cross-attention  256 x 1500: 143 us vs 112 us;  448 x 1500: 262 us vs 194 us (cuDNN sm100) -> torch SDPA
+#   causal self      128 x 128:   23 us vs  25 us;  448 x 448:   93 us vs  97 us               -> libsar
+#   encoder self    1500 x 1500: 762 us vs 540 us                                              -> torch SDPA
+# SAR_OWN_ATTN_MAX_TQ overrides both limits: =100000 puts every attention on libsar, =0 none.
+_own_env = os.environ.get("SAR_OWN_ATTN_MAX_TQ")
+OWN_ATTN_MAX_TQ = int(_own_env) if _own_env is not None else 128          # non-causal: query rows per head
+OWN_ATTN_MAX_TQ_CAUSAL = int(_own_env) if _own_env is not None else 512   # causal (square) self-attention
 
 
 def _sdpa(q, k, v, mask=None, causal=False):
     # q is pre-scaled inside the projection epilogue (HF applies `* self.scaling` to q_proj's output, then scale=1)
     causal = causal and mask is None and q.shape[2] > 1
-    if mask is None and q.shape[2] <= OWN_ATTN_MAX_TQ and (not causal or q.shape[2] == k.shape[2]):
-        return ops.attn_fwd(q, k, v, causal)
+    if mask is None:
+        tq = q.shape[2]
+        if (not causal and tq <= OWN_ATTN_MAX_TQ) or (causal and tq == k.shape[2] and tq <= OWN_ATTN_MAX_TQ_CAUSAL):
+            return ops.attn_fwd(q, k, v, causal)
     return F.scaled_dot_product_attention(q, k, v, attn_mask=mask, is_causal=causal, scale=1.0)
 
 

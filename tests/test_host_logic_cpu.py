@@ -201,24 +201,31 @@ def test_whisper_lora_wrapper_api_offline(monkeypatch):
     assert sar.get_model_info("whisper-small")["hidden_size"] == 768
 
 
-def test_attention_dispatch_picks_the_own_kernel_for_decoder_shapes_only(monkeypatch):
-    """whisper_blocks._sdpa: libsar's attention kernel up to OWN_ATTN_MAX_TQ query rows and only without an explicit mask
-    (causal only when square); everything else — the 1500 x 1500 encoder attention — goes to torch SDPA."""
+def test_attention_dispatch_picks_the_own_kernel_where_it_measured_faster(monkeypatch):
+    """whisper_blocks._sdpa: libsar's attention kernel for one query tile per head (<= 128 rows) and for causal
+    self-attention up to 512 rows, only without an explicit mask; everything else — longer cross-attention, the
+    1500 x 1500 encoder attention — goes to torch SDPA."""
     from speech_adapter_routing_b200 import ops, whisper_blocks as wb
 
     calls = []
     monkeypatch.setattr(ops, "attn_fwd", lambda q, k, v, causal: calls.append(("own", bool(causal))) or q)
     monkeypatch.setattr(wb.F, "scaled_dot_product_attention",
                         lambda q, k, v, attn_mask=None, is_causal=False, scale=None: calls.append(("torch", bool(is_causal))) or q)
-    monkeypatch.setattr(wb, "OWN_ATTN_MAX_TQ", 256)
+    monkeypatch.setattr(wb, "OWN_ATTN_MAX_TQ", 128)
+    monkeypatch.setattr(wb, "OWN_ATTN_MAX_TQ_CAUSAL", 512)
     t = lambda tq: torch.zeros(1, 2, tq, 64)
-    wb._sdpa(t(128), t(1500), t(1500))                              # decoder cross-attention
+    wb._sdpa(t(128), t(1500), t(1500))                              # decoder cross-attention, T_dec = 128
     wb._sdpa(t(128), t(128), t(128), causal=True)                   # decoder self-attention
+    wb._sdpa(t(448), t(448), t(448), causal=True)                   # ... at the maximum target length
     wb._sdpa(t(1), t(77), t(77), causal=True)                       # one query row: the causal mask is a no-op
+    wb._sdpa(t(448), t(1500), t(1500))                              # long cross-attention
     wb._sdpa(t(1500), t(1500), t(1500))                             # encoder self-attention
     wb._sdpa(t(128), t(128), t(128), mask=torch.zeros(1, 1, 128, 128), causal=True)   # explicit mask
-    assert calls == [("own", False), ("own", True), ("own", False), ("torch", False), ("torch", False)]
+    assert calls == [("own", False), ("own", True), ("own", True), ("own", False), ("torch", False), ("torch", False),
+                     ("torch", False)]
     monkeypatch.setattr(wb, "OWN_ATTN_MAX_TQ", 0)
+    monkeypatch.setattr(wb, "OWN_ATTN_MAX_TQ_CAUSAL", 0)
     calls.clear()
     wb._sdpa(t(128), t(1500), t(1500))
-    assert calls == [("torch", False)]
+    wb._sdpa(t(128), t(128), t(128), causal=True)
+    assert calls == [("torch", False), ("torch", True)]

@@ -429,7 +429,9 @@ def suite_attn():
         log(f"[attn] B={B} H={H} Tq={Tq} Tk={Tk} causal={causal}: max_abs={mx:.4g} rel={rel:.3g} {'OK' if good else 'FAIL'}")
     # perf at the bench shapes
     for (B, H, Tq, Tk, causal, name) in [(64, 12, 1500, 1500, False, "encoder self"), (64, 12, 128, 1500, False, "decoder cross"),
-                                         (64, 12, 128, 128, True, "decoder self (causal)"), (64, 20, 1500, 1500, False, "large-v3 encoder")]:
+                                         (64, 12, 128, 128, True, "decoder self (causal)"), (64, 20, 1500, 1500, False, "large-v3 encoder"),
+                                         (64, 12, 256, 1500, False, "decoder cross, 256 tokens"), (64, 12, 448, 1500, False, "decoder cross, 448 tokens"),
+                                         (64, 12, 448, 448, True, "decoder self, 448 tokens (causal)"), (16, 12, 448, 1500, False, "decoder cross, 448 tokens, B=16")]:
         q = (torch.randn(B, H, Tq, 64, device=DEV) * 0.35).to(torch.bfloat16)
         k = torch.randn(B, H, Tk, 64, device=DEV, dtype=torch.bfloat16)
         v = torch.randn(B, H, Tk, 64, device=DEV, dtype=torch.bfloat16)
