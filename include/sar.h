@@ -162,6 +162,23 @@ int sar_decode_self_attn(const void* q, const void* k_new, const void* v_new, vo
 int sar_decode_cross_attn(const void* q, const void* k, const void* v, void* out, int B, int H, int head_dim, int Tk,
                           void* stream);
 
+/*
+ * Whisper's log-mel front-end: waveform -> input_features, one launch sequence for the whole batch.
+ *   frames of 400 samples every 160 (reflect-padded by 200, the last frame dropped), periodic Hann window, |DFT|^2 over
+ *   201 bins, mel filterbank, log10(max(., 1e-10)), clamp to (clip maximum - 8), (x + 4) / 4
+ * Replaces the per-example CPU call processor.feature_extractor(audio_array, ...) of src/data/dataset.py:124-128
+ * ($HF/models/whisper/feature_extraction_whisper.py:105-135).  fp32 arithmetic on CUDA cores (see logmel.cu for why).
+ *   wave         f32 [B, n_samples]   already padded / cut to the clip length (480000 for 30 s); n_samples % 160 == 0
+ *   window       f32 [400]            0.5 - 0.5 cos(2 pi n / 400)
+ *   cos_table, sin_table  f32 [400]   cos / sin(2 pi j / 400)
+ *   mel_filters  f32 [201, n_mels]    as WhisperFeatureExtractor.mel_filters (Slaney scale and norm)
+ *   raw_ws       f32 [B, n_mels, n_samples / 160]   workspace;  clip_max_ws  int32 [B]  workspace
+ *   out          bf16 or f32 [B, n_mels, n_samples / 160]
+ */
+int sar_logmel_fwd(const float* wave, const float* window, const float* cos_table, const float* sin_table,
+                   const float* mel_filters, float* raw_ws, int32_t* clip_max_ws, void* out, int B, int n_samples,
+                   int n_mels, int out_bf16, void* stream);
+
 /* epilogue activations of sar_linear_fwd */
 #define SAR_ACT_NONE 0
 #define SAR_ACT_GELU 1 /* erf-form GELU, HF ACT2FN["gelu"] */

@@ -5,6 +5,7 @@ LoRA-only backward.  Python keeps the reference's public API; the arithmetic run
 Reference module  ->  module here
   src/models/whisper_lora.py     ->  whisper_adapters.py  (WhisperLoRA, create_whisper_lora, load_whisper_lora_from_checkpoint)
   src/models/adapter_router.py   ->  lid_router.py        (LanguageClassifier, EncoderFeatureExtractor, AdapterRouter)
+  src/data/dataset.py:124-128    ->  logmel.py            (log_mel_spectrogram: the feature extractor, batched, on the GPU)
   src/models/base.py             ->  whisper_base.py      (load_base_model, get_processor, get_model_name, get_model_info)
   peft (third party)             ->  peft_compat.py       (LoraConfig, get_peft_model, PeftModel) + lora_linear.py
 """
@@ -16,11 +17,12 @@ from .whisper_adapters import WhisperLoRA, create_whisper_lora, load_whisper_lor
 from .lid_router import AdapterRouter, EncoderFeatureExtractor, LanguageClassifier
 from .routing import base_only, current_utt_adapter, route, route_base
 from .whisper_blocks import install_fused_blocks, uninstall_fused_blocks
+from .logmel import log_mel_spectrogram
 
 __all__ = [
     "WhisperLoRA", "create_whisper_lora", "load_whisper_lora_from_checkpoint", "load_base_model", "get_processor",
     "get_model_name", "get_model_info", "whisper_config", "MODEL_NAME_MAP", "LANGUAGE_CODES",
     "LanguageClassifier", "EncoderFeatureExtractor", "AdapterRouter", "RoutedLoRALinear", "LoraConfig", "PeftModel",
     "get_peft_model", "inject_lora", "lora_modules", "route", "route_base", "base_only", "current_utt_adapter",
-    "install_fused_blocks", "uninstall_fused_blocks",
+    "install_fused_blocks", "uninstall_fused_blocks", "log_mel_spectrogram",
 ]

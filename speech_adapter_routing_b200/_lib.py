@@ -37,6 +37,7 @@ _SIGNATURES = {
     "sar_attn_fwd": (c_int, [c_void_p] * 4 + [c_int] * 6 + [c_void_p]),
     "sar_decode_self_attn": (c_int, [c_void_p] * 7 + [c_int] * 4 + [c_void_p]),
     "sar_decode_cross_attn": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_void_p]),
+    "sar_logmel_fwd": (c_int, [c_void_p] * 8 + [c_int] * 4 + [c_void_p]),
     "sar_layernorm_fwd": (c_int, [c_void_p] * 4 + [c_int64, c_int, c_float, c_void_p]),
     "sar_qv_lora_fwd_rows": (c_int, [c_void_p] * 5 + [c_void_p, c_void_p] + [c_int] * 5 + [c_float, c_void_p, c_void_p]),
     "sar_router_fwd": (c_int, [c_void_p, c_int] + [c_void_p] * 12 + [c_int] * 6 + [c_void_p] * 5 + [c_void_p, c_void_p]),

@@ -35,7 +35,6 @@ constexpr int FA_BK = 64;
 constexpr int FA_HD = 64;
 constexpr int FA_Q_BYTES = FA_BQ * FA_HD * 2;    // 16 KB
 constexpr int FA_KV_BYTES = FA_BK * FA_HD * 2;   // 8 KB
-constexpr int FA_P_BYTES = FA_BQ * FA_BK * 2;    // 16 KB
 constexpr int FA_STAGES = 5;
 
 struct FaParams {

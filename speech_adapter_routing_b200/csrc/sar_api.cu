@@ -254,6 +254,15 @@ int sar_decode_cross_attn(const void* q, const void* k, const void* v, void* out
   return decode_cross_attn(q, k, v, out, B, H, head_dim, Tk, static_cast<cudaStream_t>(stream));
 }
 
+int sar_logmel_fwd(const float* wave, const float* window, const float* cos_table, const float* sin_table,
+                   const float* mel_filters, float* raw_ws, int32_t* clip_max_ws, void* out, int B, int n_samples,
+                   int n_mels, int out_bf16, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  return logmel_fwd(wave, window, cos_table, sin_table, mel_filters, raw_ws, reinterpret_cast<int*>(clip_max_ws), out, B,
+                    n_samples, n_mels, out_bf16, static_cast<cudaStream_t>(stream));
+}
+
 int sar_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, int64_t M, int d, float eps,
                       void* stream) {
   int rc = require_sm100();

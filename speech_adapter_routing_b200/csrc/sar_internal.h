@@ -80,6 +80,9 @@ int decode_self_attn(const void* q, const void* k_new, const void* v_new, void* 
                      const long long* pos, void* out, int B, int H, int head_dim, int t_max, cudaStream_t stream);
 int decode_cross_attn(const void* q, const void* k, const void* v, void* out, int B, int H, int head_dim, int Tk,
                       cudaStream_t stream);
+int logmel_fwd(const float* wave, const float* window, const float* cos_t, const float* sin_t, const float* filters,
+               float* raw_ws, int* clip_max_ws, void* out, int B, int n_samples, int n_mels, int out_bf16,
+               cudaStream_t stream);
 int layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, int64_t M, int d, float eps,
                   cudaStream_t stream);
 

@@ -14,7 +14,7 @@ from ._lib import SAR_FLAG_SAVE_U, SAR_RPAD, check, lib
 
 
 # ---- instrumentation used by bench.py: kernel-launch counts and (optional) per-launch CUDA-event timing ----------
-LAUNCHES = {"k1": 0, "k2": 0, "k3": 0, "rows": 0, "proj": 0, "linear": 0, "ln": 0, "attn": 0}   # kernels launched by libsar, by op (k2 = 2, k3 = 3, rows = 2)
+LAUNCHES = {"k1": 0, "k2": 0, "k3": 0, "rows": 0, "proj": 0, "linear": 0, "ln": 0, "attn": 0, "logmel": 0}   # kernels launched by libsar, by op (k2 = 2, k3 = 3, rows = 2)
 SPLIT_MIN_ROWS = int(__import__("os").environ.get("SAR_SPLIT_MIN_ROWS", "4096"))   # fewer rows: single-launch LoRA kernel (M = 8192, 768 -> 2304: split 79 us, single launch 91 us)
 K1_TIMELINE = None   # set to a list to record (B*T, d_in, d_out, r, has_lora, start_event, end_event) per K1 call
 
@@ -312,6 +312,33 @@ def decode_cross_attn(q: torch.Tensor, k: torch.Tensor, v: torch.Tensor) -> torc
     out = torch.empty(B, H * hd, dtype=torch.bfloat16, device=q.device)
     check(lib().sar_decode_cross_attn(_ptr(q), _ptr(k), _ptr(v), _ptr(out), B, H, hd, Tk, _stream(q)))
     LAUNCHES["attn"] += 1
+    return out
+
+
+def logmel_fwd(wave: torch.Tensor, window: torch.Tensor, cos_table: torch.Tensor, sin_table: torch.Tensor,
+               mel_filters: torch.Tensor, out_dtype: torch.dtype = torch.bfloat16) -> torch.Tensor:
+    """Log-mel front-end (sar_logmel_fwd): wave fp32 [B, n_samples] (n_samples a multiple of 160, already padded / cut),
+    tables fp32 on the same device; returns [B, n_mels, n_samples / 160] in bf16 or fp32."""
+    _need_cuda(wave, window, cos_table, sin_table, mel_filters)
+    for t, name in ((wave, "wave"), (window, "window"), (cos_table, "cos_table"), (sin_table, "sin_table"),
+                    (mel_filters, "mel_filters")):
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise ValueError(f"{name} must be contiguous fp32")
+    if wave.dim() != 2 or wave.shape[1] % 160 or window.numel() != 400 or cos_table.numel() != 400 or sin_table.numel() != 400:
+        raise ValueError("wave must be [B, n_samples] with n_samples % 160 == 0; window / tables have 400 entries")
+    if mel_filters.dim() != 2 or mel_filters.shape[0] != 201:
+        raise ValueError("mel_filters must be [201, n_mels]")
+    if out_dtype not in (torch.bfloat16, torch.float32):
+        raise ValueError("out_dtype must be bfloat16 or float32")
+    B, n_samples = wave.shape
+    n_mels, n_frames = mel_filters.shape[1], n_samples // 160
+    raw = torch.empty(B, n_mels, n_frames, dtype=torch.float32, device=wave.device)
+    clip_max = torch.empty(B, dtype=torch.int32, device=wave.device)
+    out = torch.empty(B, n_mels, n_frames, dtype=out_dtype, device=wave.device)
+    check(lib().sar_logmel_fwd(_ptr(wave), _ptr(window), _ptr(cos_table), _ptr(sin_table), _ptr(mel_filters), _ptr(raw),
+                               _ptr(clip_max), _ptr(out), B, n_samples, n_mels, int(out_dtype == torch.bfloat16),
+                               _stream(wave)))
+    LAUNCHES["logmel"] += 3
     return out
 
 

@@ -229,3 +229,26 @@ def test_attention_dispatch_picks_the_own_kernel_where_it_measured_faster(monkey
     wb._sdpa(t(128), t(1500), t(1500))
     wb._sdpa(t(128), t(128), t(128), causal=True)
     assert calls == [("torch", False), ("torch", True)]
+
+
+def test_logmel_host_tables_match_the_feature_extractor_and_padding_rules():
+    """speech_adapter_routing_b200.logmel (host side of sar_logmel_fwd): its own Slaney filterbank equals
+    WhisperFeatureExtractor.mel_filters, the window is the periodic Hann of torch.hann_window, and clips are zero-padded
+    on the right / cut to 30 s like the feature extractor does."""
+    import numpy as np
+    from transformers import WhisperFeatureExtractor
+
+    from speech_adapter_routing_b200 import logmel
+
+    for n_mels in (80, 128):
+        fe = WhisperFeatureExtractor(feature_size=n_mels)
+        assert np.abs(logmel.mel_filterbank(n_mels).numpy() - fe.mel_filters).max() <= 1e-12
+    window, cos_t, sin_t, filt = logmel.tables("cpu", 80)
+    assert torch.allclose(window, torch.hann_window(400), atol=1e-7)
+    j = torch.arange(400, dtype=torch.float64)
+    assert torch.allclose(cos_t.double() ** 2 + sin_t.double() ** 2, torch.ones(400, dtype=torch.float64), atol=1e-6)
+    assert filt.shape == (201, 80) and filt.dtype == torch.float32
+    x = logmel.pad_or_trim([torch.ones(10), torch.ones(logmel.N_SAMPLES + 5)])
+    assert x.shape == (2, logmel.N_SAMPLES) and x[0, :10].sum() == 10 and x[0, 10:].abs().sum() == 0 and x[1].min() == 1
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        logmel.log_mel_spectrogram(torch.zeros(2, 16000))

@@ -227,3 +227,33 @@ def test_k3_is_deterministic(cuda_dev):
                              Bm.transpose(1, 2).contiguous(), ia, dA, dB, c.scaling)
         outs.append((dx.clone(), dA.clone(), dB.clone()))
     assert all(torch.equal(a, b) for a, b in zip(*outs))      # fixed-order reductions, no float atomics
+
+
+# ------------------------------------------------------------------------------------------------ log-mel front-end
+@pytest.mark.parametrize("n_mels,dtype,tol", [(80, torch.float32, 2e-3), (128, torch.float32, 2e-3), (80, torch.bfloat16, 1e-2)])
+def test_logmel_matches_oracle(cuda_dev, n_mels, dtype, tol):
+    """sar_logmel_fwd (waveform -> input_features on the GPU) vs the float64 oracle that is pinned against
+    WhisperFeatureExtractor: a tone in noise (5 s, padded), over-long noise (cut at 30 s), a click in silence, and an
+    all-zero clip.  fp32 output within 2e-3 absolute (values span about [-1.5, 1.5]); bf16 output adds one rounding."""
+    import numpy as np
+
+    from oracle import logmel as ologmel
+    from speech_adapter_routing_b200 import logmel
+
+    rng = np.random.default_rng(3)
+    t = np.arange(16000 * 5) / 16000.0
+    clips = [
+        (0.3 * np.sin(2 * np.pi * 440.0 * t) + 0.05 * rng.standard_normal(t.shape)).astype(np.float32),
+        (0.1 * rng.standard_normal(16000 * 31)).astype(np.float32),
+        np.concatenate([np.zeros(8000, np.float32), np.ones(1, np.float32), np.zeros(4000, np.float32)]),
+        np.zeros(16000, np.float32),
+    ]
+    out = logmel.log_mel_spectrogram([torch.from_numpy(c).to(cuda_dev) for c in clips], n_mels=n_mels, dtype=dtype)
+    assert out.shape == (len(clips), n_mels, 3000) and out.dtype == dtype
+    for i, c in enumerate(clips):
+        ref = torch.from_numpy(ologmel.log_mel(c, n_mels))
+        err = (out[i].double().cpu() - ref).abs().max().item()
+        assert err <= tol, f"clip {i}: max abs err {err}"
+    # a clip processed alone gives identical values (the per-clip maximum never leaks across clips)
+    one = logmel.log_mel_spectrogram([torch.from_numpy(clips[0]).to(cuda_dev)], n_mels=n_mels, dtype=dtype)
+    assert torch.equal(one[0], out[0])

@@ -163,6 +163,29 @@ def test_attention_oracle_reproduces_hf_eager_attention_with_and_without_the_cau
     assert torch.allclose(one[:, :, 0], full[:, :, pos], atol=1e-6)
 
 
+def test_logmel_oracle_reproduces_hf_whisper_feature_extractor():
+    """oracle.logmel is pinned against the installed WhisperFeatureExtractor — what the reference's data path calls per
+    example (src/data/dataset.py:124-128): filterbank identical, features of a short (padded) and an over-long (cut)
+    clip within float32 resolution of HF's float32 output, for 80 and 128 mel bins."""
+    import numpy as np
+    from transformers import WhisperFeatureExtractor
+
+    from oracle import logmel as ologmel
+
+    rng = np.random.default_rng(7)
+    t = np.arange(16000 * 5) / 16000.0
+    short = (0.3 * np.sin(2 * np.pi * 440.0 * t) + 0.05 * rng.standard_normal(t.shape)).astype(np.float32)
+    long = (0.1 * rng.standard_normal(16000 * 31)).astype(np.float32)
+    for n_mels in (80, 128):
+        fe = WhisperFeatureExtractor(feature_size=n_mels)
+        assert np.abs(ologmel.mel_filterbank(n_mels) - fe.mel_filters).max() <= 1e-12
+        for wave in (short, long):
+            ref = fe(wave, sampling_rate=16000, return_tensors="np").input_features[0]
+            got = ologmel.log_mel(wave, n_mels)
+            assert got.shape == ref.shape == (n_mels, 3000)
+            assert np.abs(got - ref).max() <= 5e-5
+
+
 def test_lora_oracle_agrees_with_an_independent_multi_lora_restatement():
     """Second opinion for the UNPINNED LoRA oracle: vLLM's pure-torch multi-LoRA ops (vllm/lora/ops/torch_ops/lora_ops.py,
     an independent restatement of PEFT's y = base + scaling * B(A(x)) with per-sequence adapter indices, installed in
