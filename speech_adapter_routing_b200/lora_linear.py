@@ -197,12 +197,7 @@ class RoutedLoRALinear(nn.Module):
             x3 = x3.to(torch.bfloat16)
         B, T = x3.shape[0], x3.shape[1]
         idx = self.resolve_index(B, x3.device)
-        if self.training and idx is not None:
-            name = self.active_adapter
-            if isinstance(self.lora_dropout[name], nn.Dropout) and self.lora_dropout[name].p > 0:
-                raise NotImplementedError(
-                    "lora_dropout > 0 in training mode is not fused yet: construct with lora_dropout=0.0 "
-                    "(reference default 0.1 applies dropout to the A-branch input only)")
+        drop_fix = self.training and idx is not None and self._dropout_active()
         need_grad = torch.is_grad_enabled() and idx is not None and (
             x3.requires_grad or any(p.requires_grad for p in self.lora_A.parameters()) or
             any(p.requires_grad for p in self.lora_B.parameters()))
@@ -217,8 +212,31 @@ class RoutedLoRALinear(nn.Module):
             else:
                 y, _ = ops.qv_lora_fwd(x3, st["W"], st["bias"], st["A"] if idx is not None else None,
                                        st["Bp"] if idx is not None else None, idx, st["scale"])
+        if drop_fix:
+            y = y + self._dropout_correction(x3, idx).to(y.dtype)
         y = y.reshape(*lead, self.out_features)
         return y if in_dtype == torch.bfloat16 else y.to(in_dtype)
+
+    # ------------------------------------------------------------------ lora_dropout > 0 (training mode only)
+    def _dropout_active(self) -> bool:
+        d = self.lora_dropout[self.active_adapter] if self.active_adapter in self.lora_dropout else None
+        return isinstance(d, nn.Dropout) and d.p > 0
+
+    def _dropout_correction(self, x3: torch.Tensor, idx: torch.Tensor) -> torch.Tensor:
+        """PEFT drops the input of the A branch only: y = base(x) + s·B(A(drop(x))) (reference default p = 0.1,
+        src/models/whisper_lora.py:30, scripts/train_lora.py:55).  The fused kernels compute base(x) + s·B(A(x)); this adds
+        the zero-mean remainder s·B(A(drop(x) - x)) with plain autograd ops (two skinny GEMMs per adapter in use), so
+        K1 / K3 stay on the main path and the sum is exactly PEFT's formula.  Utterance b uses adapter idx[b] (< 0: none);
+        the mask is drawn once per call from the active adapter's Dropout module."""
+        drop = self.lora_dropout[self.active_adapter]
+        rem = drop(x3) - x3                                            # [B, T, d_in]: -x where dropped, x·p/(1-p) where kept
+        out = None
+        for k, name in enumerate(self.adapter_order):
+            A, Bw = self.lora_A[name].weight, self.lora_B[name].weight
+            sel = (idx == k).to(A.dtype).view(-1, 1, 1)                # no host sync: adapters not in the batch add zeros
+            term = torch.nn.functional.linear(torch.nn.functional.linear(rem.to(A.dtype), A), Bw) * (self.scaling[name] * sel)
+            out = term if out is None else out + term
+        return out
 
     # ------------------------------------------------------------------ merge (PEFT merge_and_unload semantics)
     @torch.no_grad()

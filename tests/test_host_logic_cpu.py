@@ -252,3 +252,39 @@ def test_logmel_host_tables_match_the_feature_extractor_and_padding_rules():
     assert x.shape == (2, logmel.N_SAMPLES) and x[0, :10].sum() == 10 and x[0, 10:].abs().sum() == 0 and x[1].min() == 1
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         logmel.log_mel_spectrogram(torch.zeros(2, 16000))
+
+
+def test_lora_dropout_correction_completes_pefts_formula():
+    """lora_dropout > 0 in training mode (the reference's default 0.1): the fused kernels give base(x) + s·B(A(x)) and
+    RoutedLoRALinear adds s·B(A(drop(x) - x)); the sum must be PEFT's base(x) + s·B(A(drop(x))) for the mask that was
+    drawn, per utterance adapter, with gradients reaching A and B.  (Pure torch, so it is checked here on the CPU.)"""
+    from speech_adapter_routing_b200.lora_linear import RoutedLoRALinear
+
+    torch.manual_seed(0)
+    base = nn.Linear(32, 48)
+    m = RoutedLoRALinear(base, "hindi", r=4, lora_alpha=8, lora_dropout=0.25)
+    m.add_adapter("telugu", 8, 16, 0.25)
+    for name in ("hindi", "telugu"):
+        nn.init.normal_(m.lora_B[name].weight, std=0.1)
+    m.train()
+    assert m._dropout_active()
+    x = torch.randn(3, 5, 32)
+    idx = torch.tensor([1, -1, 0], dtype=torch.int32)
+    torch.manual_seed(123)
+    corr = m._dropout_correction(x, idx)
+    torch.manual_seed(123)
+    xd = m.lora_dropout["hindi"](x)                      # the same mask
+    assert (xd == 0).any() and not torch.equal(xd, x)
+    for b, k in enumerate(idx.tolist()):
+        if k < 0:
+            assert corr[b].abs().max() == 0
+            continue
+        name = m.adapter_order[k]
+        A, Bw, s_ = m.lora_A[name].weight, m.lora_B[name].weight, m.scaling[name]
+        fused = base(x[b]) + s_ * (x[b] @ A.t()) @ Bw.t()            # what K1 computes
+        peft = base(x[b]) + s_ * (xd[b] @ A.t()) @ Bw.t()            # PEFT lora.Linear.forward in training mode
+        assert torch.allclose(fused + corr[b], peft, atol=1e-5)
+    corr.sum().backward()
+    assert m.lora_A["hindi"].weight.grad.abs().sum() > 0 and m.lora_B["telugu"].weight.grad.abs().sum() > 0
+    m.eval()
+    assert not (m.training and m._dropout_active())      # eval: no correction, the kernels' result is PEFT's

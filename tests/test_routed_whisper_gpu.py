@@ -320,3 +320,37 @@ def test_config1_whisper_small_single_adapter_one_clip(cuda_dev, tmp_path):
         gap = (lg[t].max() - lg[t, got[0, t]]).item()
         assert gap <= LOGIT_TOL * lg.abs().max().item(), (t, gap, got.tolist(), want.tolist())
     assert got.shape[0] == 1 and got.dtype == torch.long
+
+
+def test_training_forward_backward_with_lora_dropout_matches_pefts_formula(cuda_dev):
+    """The reference trains with lora_dropout = 0.1 (scripts/train_lora.py:55).  In training mode the module output
+    must be base(x) + s·B(A(drop(x))) for the mask drawn in that call (K1 + the autograd correction term), and the
+    backward (K3 + autograd) must give the gradients of that expression."""
+    import torch.nn as nn
+
+    from speech_adapter_routing_b200.lora_linear import RoutedLoRALinear
+
+    torch.manual_seed(3)
+    d, r, p = 384, 16, 0.1
+    base = nn.Linear(d, d).to(cuda_dev).to(torch.bfloat16)
+    m = RoutedLoRALinear(base, "hindi", r=r, lora_alpha=2 * r, lora_dropout=p).to(cuda_dev)
+    nn.init.normal_(m.lora_B["hindi"].weight, std=0.05)
+    m.train()
+    x = (torch.randn(4, 200, d, device=cuda_dev) * 0.5).to(torch.bfloat16).requires_grad_(True)
+    torch.manual_seed(77)
+    y = m(x)
+    dy = torch.randn_like(y)
+    y.backward(dy)
+    gA, gB, gx = m.lora_A["hindi"].weight.grad.float().clone(), m.lora_B["hindi"].weight.grad.float().clone(), x.grad.float().clone()
+
+    xr = x.detach().float().requires_grad_(True)
+    A = m.lora_A["hindi"].weight.detach().float().requires_grad_(True)
+    Bw = m.lora_B["hindi"].weight.detach().float().requires_grad_(True)
+    torch.manual_seed(77)
+    mask = nn.functional.dropout(torch.ones_like(x), p=p, training=True).float()     # same generator state, same shape/dtype
+    ref = nn.functional.linear(xr, base.weight.float(), base.bias.float()) + 2.0 * ((xr * mask) @ A.t()) @ Bw.t()
+    ref.backward(dy.float())
+    rel = lambda a, b: ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+    assert rel(y.detach().float(), ref.detach()) <= 2.0 ** -6
+    assert rel(gx, xr.grad) <= 2.0 ** -5
+    assert rel(gA, A.grad) <= 2.0 ** -5 and rel(gB, Bw.grad) <= 2.0 ** -5
