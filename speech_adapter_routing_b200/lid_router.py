@@ -156,11 +156,19 @@ class LanguageClassifier(nn.Module):
 
     @torch.no_grad()
     def route_batch(self, encoder_hidden_states: torch.Tensor) -> ops.RouterOut:
-        """K2 on the default architecture: logits, probs, idx (int32, device), perm, seg_starts — no host sync."""
-        if not self._k2_eligible(None):
-            raise NotImplementedError("the fused router kernel covers the reference's default LID architecture "
-                                      "(mean pooling, LayerNorm, no CNN, two hidden layers)")
-        return ops.router_fwd(encoder_hidden_states, self._k2_params(encoder_hidden_states.device))
+        """logits, probs, idx (int32, device), perm, seg_starts — no host sync.  The default architecture on a CUDA
+        device runs the K2 kernel; the reference's other LID variants (CNN front-end, max / attention pooling, other
+        depths: src/models/adapter_router.py:210-249, 271-275) run their torch graph and get the same bookkeeping
+        (stable sort by adapter index, segment starts) from device-side torch ops."""
+        if encoder_hidden_states.is_cuda and self._k2_eligible(None) and not self.training:
+            return ops.router_fwd(encoder_hidden_states, self._k2_params(encoder_hidden_states.device))
+        out = self.forward(encoder_hidden_states)
+        logits, probs = out["logits"].float(), out["probs"].float()
+        idx = probs.argmax(dim=-1)
+        perm = torch.sort(idx, stable=True).indices
+        counts = torch.bincount(idx, minlength=probs.shape[-1])
+        seg_starts = torch.cat([counts.new_zeros(1), counts.cumsum(0)])
+        return ops.RouterOut(logits, probs, idx.to(torch.int32), perm.to(torch.int32), seg_starts.to(torch.int32))
 
     def predict(self, encoder_hidden_states: torch.Tensor,
                 attention_mask: Optional[torch.Tensor] = None) -> Tuple[torch.Tensor, torch.Tensor]:

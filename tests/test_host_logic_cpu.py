@@ -288,3 +288,20 @@ def test_lora_dropout_correction_completes_pefts_formula():
     assert m.lora_A["hindi"].weight.grad.abs().sum() > 0 and m.lora_B["telugu"].weight.grad.abs().sum() > 0
     m.eval()
     assert not (m.training and m._dropout_active())      # eval: no correction, the kernels' result is PEFT's
+
+
+def test_route_batch_covers_the_non_default_lid_architectures_on_the_torch_graph():
+    """LanguageClassifier.route_batch: the K2 kernel serves the default architecture on a GPU; max / attention pooling
+    and the CNN front-end (reference src/models/adapter_router.py:210-249, 271-275) run the torch graph and still get
+    idx / perm / seg_starts (stable sort by adapter index) without a host round trip."""
+    torch.manual_seed(4)
+    h = torch.randn(6, 40, 32)
+    for kw in ({"pooling": "max"}, {"pooling": "attention"}, {"use_cnn": True, "cnn_channels": 16}):
+        clf = sar.LanguageClassifier(input_dim=32, num_classes=3, languages=["a", "b", "c"], **kw).eval()
+        out = clf.route_batch(h)
+        labels, probs = clf.predict(h)
+        assert torch.equal(out.idx.long(), labels) and torch.allclose(out.probs, probs.float())
+        assert out.idx.dtype == torch.int32 and out.perm.dtype == torch.int32 and out.seg_starts.dtype == torch.int32
+        exp_perm = sorted(range(6), key=lambda i: (int(labels[i]), i))
+        assert out.perm.tolist() == exp_perm
+        assert out.seg_starts.tolist() == [0] + torch.bincount(labels, minlength=3).cumsum(0).tolist()
