@@ -226,9 +226,10 @@ def build_b200_workload(dev, seed):
     for lang in LANGUAGES:
         sar.inject_lora(model, lcfg, adapter_name=lang)
     g = torch.Generator(device="cpu").manual_seed(seed)
-    for m in sar.lora_modules(model).values():
-        for lang in LANGUAGES:   # PEFT's zero-init lora_B would make the adapter path a no-op numerically
-            m.lora_B[lang].weight.data.copy_((torch.randn(m.out_features, RANK_R, generator=g) * 0.02).to(dev))
+    with torch.no_grad():
+        for m in sar.lora_modules(model).values():
+            for lang in LANGUAGES:   # PEFT's zero-init lora_B would make the adapter path a no-op numerically
+                m.lora_B[lang].weight.copy_((torch.randn(m.out_features, RANK_R, generator=g) * 0.02).to(dev))
     clf = sar.LanguageClassifier(input_dim=cfg.d_model, num_classes=N_ADAPTERS, languages=LANGUAGES).to(dev).eval()
     router = sar.AdapterRouter.from_stacked(model, clf, LANGUAGES, strategy="hard").eval()
 

@@ -31,7 +31,8 @@ from . import lora as olora
 from . import router as orouter
 
 GEOMETRY = {  # d_model, layers, heads, ffn, mel bins, vocab
-    "micro": (128, 2, 4, 256, 80, 1024),      # test-only geometry (seconds on a CPU)
+    "micro": (256, 2, 4, 512, 80, 1024),      # test-only geometry, head_dim 64 like every real Whisper (the fused blocks run)
+    "micro32": (128, 2, 4, 256, 80, 1024),    # test-only geometry, head_dim 32: HF layer bodies over the K1 module slots
     "tiny": (384, 4, 6, 1536, 80, 51865),
     "base": (512, 6, 8, 2048, 80, 51865),
     "small": (768, 12, 12, 3072, 80, 51865),

@@ -161,7 +161,9 @@ class StaticGreedyDecoder:
 
     def _weights_key(self) -> int:
         dec = self.model.model.decoder
-        return hash(tuple((p.data_ptr(), p._version) for p in dec.parameters()))
+        from .routing import operand_epoch
+
+        return hash(tuple((p.data_ptr(), p._version) for p in dec.parameters()) + (operand_epoch(),))
 
     # ------------------------------------------------------------------ one token step (graph-capturable)
     def _step(self, st: _State) -> None:

@@ -64,14 +64,32 @@ class FlatGradBucket:
             self.views.append(v)
             off += p.numel()
 
-    def zero_(self) -> None:
-        self.buffer.zero_()
-        for p, v in zip(self.params, self.views):   # optimizers called with set_to_none=True drop the views
+    def attach(self) -> int:
+        """Re-point every ``param.grad`` at its bucket view; returns how many had been detached.  An optimizer's
+        ``zero_grad(set_to_none=True)`` (the torch default) drops the views: autograd would then allocate fresh
+        ``.grad`` tensors and the collective would reduce a bucket of zeros."""
+        n = 0
+        for p, v in zip(self.params, self.views):
             if p.grad is None or p.grad.data_ptr() != v.data_ptr():
                 p.grad = v
+                n += 1
+        return n
+
+    def zero_(self) -> None:
+        self.buffer.zero_()
+        self.attach()
+
+    def check_attached(self) -> None:
+        """Raise if any gradient lives outside the bucket (``zero_grad(set_to_none=True)`` ran after ``zero_()``)."""
+        bad = [i for i, (p, v) in enumerate(zip(self.params, self.views))
+               if p.grad is None or p.grad.data_ptr() != v.data_ptr()]
+        if bad:
+            raise RuntimeError(f"{len(bad)} parameter gradients are not views of the flat bucket (first: #{bad[0]}); "
+                               "call bucket.zero_() / bucket.attach() AFTER optimizer.zero_grad(), before backward")
 
     def all_reduce_mean(self, group=None, async_op: bool = False):
         """Sum the bucket over ranks (one collective), then scale by 1/world.  Returns a work handle if async."""
+        self.check_attached()
         if not dist.is_initialized() or dist.get_world_size(group) == 1:
             return None
         world = dist.get_world_size(group)

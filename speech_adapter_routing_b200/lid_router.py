@@ -24,7 +24,7 @@ import torch.nn.functional as F
 from . import ops
 from .lora_linear import RoutedLoRALinear
 from .peft_compat import LoraConfig, PeftModel, inject_lora, lora_modules
-from .routing import base_only, route, route_base
+from .routing import base_only, operand_epoch, route, route_base
 
 logger = logging.getLogger(__name__)
 
@@ -149,7 +149,8 @@ class LanguageClassifier(nn.Module):
 
     def _k2_params(self, device) -> ops.RouterParams:
         sd = self.state_dict()
-        key = tuple((v.data_ptr(), v._version) for k, v in sd.items() if k != "_class_weights") + (str(device),)
+        key = tuple((v.data_ptr(), v._version) for k, v in sd.items() if k != "_class_weights") + (str(device),
+                                                                                                     operand_epoch())
         if self._router_params is None or self._router_params[0] != key:
             self._router_params = (key, ops.RouterParams.from_state_dict(sd, device))
         return self._router_params[1]
@@ -199,7 +200,9 @@ class LanguageClassifier(nn.Module):
 
     @classmethod
     def load(cls, load_path: Union[str, Path], device: Optional[str] = None) -> "LanguageClassifier":
-        ckpt = torch.load(Path(load_path), map_location=device or "cpu", weights_only=False)
+        # tensors + a dict of str / int / float / list only: the safe (weights_only) loader is enough, and a router
+        # checkpoint is user-supplied input (the reference's plain torch.load is weights_only=True on torch >= 2.6)
+        ckpt = torch.load(Path(load_path), map_location=device or "cpu", weights_only=True)
         cfg = ckpt.get("config", {})
         clf = cls(input_dim=cfg.get("input_dim", 768), num_classes=cfg.get("num_classes", 4),
                   pooling=cfg.get("pooling", "mean"), use_cnn=cfg.get("use_cnn", False),
@@ -303,6 +306,15 @@ class AdapterRouter(nn.Module):
         self.strategy = strategy
         self.threshold = threshold
         self.lang_to_idx = {lang: i for i, lang in enumerate(self.languages)}
+        # The reference indexes ``self.languages[label]`` (:565) and raises IndexError for a class without a language;
+        # here a class index >= n_adapters would silently run on base weights inside K1, so refuse it up front.
+        n_cls = getattr(classifier, "num_classes", None)
+        if n_cls is not None and n_cls != len(self.languages):
+            raise ValueError(f"classifier has {n_cls} classes but {len(self.languages)} languages were given")
+        clf_langs = getattr(classifier, "languages", None)
+        if clf_langs is not None and list(clf_langs) != self.languages:
+            logger.warning("classifier languages %s differ from router languages %s: class k routes to %s",
+                           list(clf_langs), self.languages, "languages[k]")
         self.whisper = _unwrap_whisper(base_model)
         for p in self.base_model.parameters():
             p.requires_grad = False
@@ -481,6 +493,10 @@ class AdapterRouter(nn.Module):
         if plan is not None:
             # one CUDA-graph'd token step for the whole mixed-language batch (decode.py)
             ids = native.generate(input_features, plan, idx)
+            if language is not None:
+                # reference :735-738 returns adapter.generate() unchanged: finished rows stay padded with HF's
+                # pad_token_id (a special token that batch_decode strips), NOT with 0 ('!')
+                return ids
             return _zero_pad_after_eos(ids, plan.eos_ids, first_is_prompt=False)
         was_ckpt = self.whisper.model.encoder.gradient_checkpointing
         if was_ckpt:
@@ -494,6 +510,8 @@ class AdapterRouter(nn.Module):
             self.whisper.config.use_cache = use_cache
             if was_ckpt:
                 self.whisper.gradient_checkpointing_enable()
+        if language is not None:
+            return ids
         return _zero_pad_after_eos(ids, self.whisper.generation_config.eos_token_id)
 
 

@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .routing import current_utt_adapter, routing_base_only
+from .routing import current_utt_adapter, operand_epoch, refresh_operands, routing_base_only
 
 
 class _QVLoRAFn(torch.autograd.Function):
@@ -100,6 +100,7 @@ class RoutedLoRALinear(nn.Module):
         if self.active_adapter is None:
             self.active_adapter = name
         self._cache.clear()
+        refresh_operands()
 
     def set_adapter(self, name: str) -> None:
         if name not in self.lora_A:
@@ -113,7 +114,7 @@ class RoutedLoRALinear(nn.Module):
     def _key(self):
         ws = [self.base_layer.weight, self.base_layer.bias] + [self.lora_A[n].weight for n in self.adapter_order] + \
              [self.lora_B[n].weight for n in self.adapter_order]
-        return tuple((w.data_ptr(), w._version) if w is not None else None for w in ws)
+        return tuple((w.data_ptr(), w._version) if w is not None else None for w in ws) + (operand_epoch(),)
 
     @torch.no_grad()
     def _stacks(self, backward: bool = False) -> Dict[str, object]:

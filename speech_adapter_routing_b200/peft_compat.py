@@ -23,6 +23,7 @@ import torch
 import torch.nn as nn
 
 from .lora_linear import RoutedLoRALinear
+from .routing import refresh_operands
 
 ADAPTER_CONFIG = "adapter_config.json"
 ADAPTER_WEIGHTS = "adapter_model.safetensors"
@@ -218,6 +219,7 @@ class PeftModel(nn.Module):
                 own[full].copy_(v.to(own[full].dtype))
         if missing:
             raise KeyError(f"adapter tensors without a matching module: {missing[:4]} ...")
+        refresh_operands()   # new adapter values: every cached bf16 operand pack / decode graph rebuilds on next use
         for n, p in own.items():
             if f".{adapter_name}." in n and (".lora_A." in n or ".lora_B." in n):
                 p.requires_grad = is_trainable

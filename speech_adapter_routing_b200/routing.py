@@ -69,3 +69,24 @@ def route(utt_adapter: Optional[torch.Tensor]):
 def base_only(batch_size: int, device) -> torch.Tensor:
     """utt_adapter selecting no adapter for every utterance (the LID feature pass runs on base weights)."""
     return torch.full((batch_size,), -1, dtype=torch.int32, device=device)
+
+
+# ---- operand-cache epoch ---------------------------------------------------------------------------------------
+# Every bf16 operand cache of the package (RoutedLoRALinear._stacks, the fused blocks' packs, the K2 parameter pack,
+# the decode graph) is keyed on (data_ptr, tensor._version) of its source parameters.  In-place ops under no_grad
+# (optimizer steps, ``copy_``, ``load_state_dict``) bump ``_version``; writes through ``param.data`` do NOT.  The
+# epoch below is part of every key: ``refresh_operands()`` bumps it, which makes every cache rebuild on next use.
+# load_adapter / add_adapter / load_state_dict paths of this package call it; user code that writes through ``.data``
+# (or through a raw pointer) must call it too.
+_operand_epoch = 0
+
+
+def operand_epoch() -> int:
+    return _operand_epoch
+
+
+def refresh_operands() -> int:
+    """Invalidate every cached bf16 operand pack and captured decode graph (call after ``param.data`` writes)."""
+    global _operand_epoch
+    _operand_epoch += 1
+    return _operand_epoch

@@ -32,13 +32,16 @@ import torch.nn.functional as F
 from . import ops
 from ._lib import SAR_ACT_GELU, SAR_ACT_NONE
 from .lora_linear import RoutedLoRALinear
+from .routing import operand_epoch
 
 FUSED_BLOCKS_ENABLED = True   # debug switch: False restores HF's layer bodies everywhere
 
 
 # ------------------------------------------------------------------------------------------------ operand packing
 def _pver(*ts) -> Tuple:
-    return tuple((t.data_ptr(), t._version) if t is not None else None for t in ts)
+    # (pointer, version) per tensor + the package-wide operand epoch (routing.refresh_operands: ``.data`` writes do
+    # not bump ``_version``)
+    return tuple((t.data_ptr(), t._version) if t is not None else None for t in ts) + (operand_epoch(),)
 
 
 def _lin_params(m: nn.Module) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
@@ -439,6 +442,10 @@ def _layer_supported(layer: nn.Module, decoder: bool) -> bool:
     if not _is_gelu(layer) or not _supported_attn(layer.self_attn):
         return False
     if decoder and not _supported_attn(layer.encoder_attn):
+        return False
+    # the fused body reads fc1 / fc2 as plain dense operands: a LoRA target there (the reference exposes
+    # --target_modules, scripts/train_lora.py:57) keeps HF's body, whose fc1 / fc2 calls go through RoutedLoRALinear
+    if type(layer.fc1) is not nn.Linear or type(layer.fc2) is not nn.Linear:
         return False
     if layer.fc1.out_features % 128 or layer.fc1.in_features % 128:
         return False

@@ -43,6 +43,24 @@ def test_flat_bucket_views_alias_param_grads():
     assert float(b.buffer.abs().sum()) == 0.0 and ps[1].grad is b.views[0]
 
 
+def test_flat_bucket_refuses_to_reduce_detached_grads():
+    """optimizer.zero_grad(set_to_none=True) after bucket.zero_() drops the views; the bucket must notice
+    instead of all-reducing zeros."""
+    ps = [torch.nn.Parameter(torch.randn(4, 3)), torch.nn.Parameter(torch.randn(5))]
+    b = FlatGradBucket(ps)
+    opt = torch.optim.SGD(ps, lr=0.1)
+    b.zero_()
+    opt.zero_grad()                                  # set_to_none=True is the default
+    (ps[0].sum() + ps[1].sum()).backward()           # grads land in fresh tensors, the bucket stays zero
+    with pytest.raises(RuntimeError, match="not views of the flat bucket"):
+        b.all_reduce_mean()
+    assert b.attach() == 2
+    b.zero_()
+    (ps[0].sum() + ps[1].sum()).backward()
+    b.all_reduce_mean()                              # world size 1: checks only
+    assert torch.equal(b.buffer, torch.ones_like(b.buffer))
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))

@@ -130,7 +130,7 @@ def test_language_classifier_checkpoint_format_and_state_dict_keys(tmp_path):
     assert set(clf.state_dict()) == set(fixtures.ROUTER_KEYS) | {"_class_weights", "loss_fn.weight"}
     assert set(sar.LanguageClassifier(input_dim=64, num_classes=4).state_dict()) == set(fixtures.ROUTER_KEYS)
     clf.save(tmp_path / "c" / "classifier.pt")
-    ck = torch.load(tmp_path / "c" / "classifier.pt", weights_only=False)
+    ck = torch.load(tmp_path / "c" / "classifier.pt", weights_only=True)
     assert set(ck) == {"state_dict", "config"}
     assert set(ck["config"]) == {"input_dim", "num_classes", "pooling", "use_cnn", "label_smoothing", "languages",
                                  "class_weights"}
@@ -305,3 +305,55 @@ def test_route_batch_covers_the_non_default_lid_architectures_on_the_torch_graph
         exp_perm = sorted(range(6), key=lambda i: (int(labels[i]), i))
         assert out.perm.tolist() == exp_perm
         assert out.seg_starts.tolist() == [0] + torch.bincount(labels, minlength=3).cumsum(0).tolist()
+
+
+def test_lora_on_fc1_fc2_keeps_hfs_layer_body(micro_model):
+    """a LoRA target on fc1 / fc2 (scripts/train_lora.py:57 exposes --target_modules) must not bind the fused
+    layer body, which reads fc1 / fc2 as plain dense operands and would drop (or crash on) the adapter term."""
+    import copy
+    from speech_adapter_routing_b200 import whisper_blocks as wb
+
+    m = copy.deepcopy(micro_model)
+    sar.inject_lora(m, sar.LoraConfig(r=8, lora_alpha=16, target_modules=["q_proj", "v_proj", "fc1", "fc2"]))
+    wb.install_fused_blocks(m)
+    for layer in list(m.model.encoder.layers) + list(m.model.decoder.layers):
+        assert isinstance(layer.fc1, sar.RoutedLoRALinear) and isinstance(layer.fc2, sar.RoutedLoRALinear)
+        assert not hasattr(layer, "_sar_pack")                       # HF's body stays
+    m2 = copy.deepcopy(micro_model)
+    sar.inject_lora(m2, sar.LoraConfig(r=8, lora_alpha=16, target_modules=["q_proj", "v_proj"]))
+    wb.install_fused_blocks(m2)
+    assert all(hasattr(l, "_sar_pack") for l in m2.model.encoder.layers)   # the default target set is bound
+
+
+def test_refresh_operands_invalidates_every_cache_key():
+    """writes through ``param.data`` do not bump ``_version``; ``refresh_operands()`` is the explicit hook and
+    load_adapter / add_adapter call it."""
+    from speech_adapter_routing_b200 import whisper_blocks as wb
+
+    lin = nn.Linear(64, 64)
+    m = sar.RoutedLoRALinear(lin, "a", r=8, lora_alpha=16)
+    k0, p0 = m._key(), wb._pver(lin.weight)
+    lin.weight.data.mul_(2.0)                                        # invisible to the version counter ...
+    assert m._key() == k0 and wb._pver(lin.weight) == p0
+    sar.refresh_operands()                                           # ... visible through the epoch
+    assert m._key() != k0 and wb._pver(lin.weight) != p0
+    k1 = m._key()
+    with torch.no_grad():
+        lin.weight.mul_(0.5)                                         # in-place op under no_grad: version bump, no hook needed
+    assert m._key() != k1
+    e = routing.operand_epoch()
+    m.add_adapter("b", 8, 16)
+    assert routing.operand_epoch() > e
+
+
+def test_adapter_router_rejects_a_classifier_with_the_wrong_class_count(micro_model):
+    import copy
+    m = copy.deepcopy(micro_model)
+    langs = ["hindi", "italian"]
+    for l in langs:
+        sar.inject_lora(m, sar.LoraConfig(r=8, lora_alpha=16, target_modules=["q_proj", "v_proj"]), adapter_name=l)
+    clf = sar.LanguageClassifier(input_dim=m.config.d_model, num_classes=3, languages=["a", "b", "c"])
+    with pytest.raises(ValueError, match="3 classes"):
+        sar.AdapterRouter.from_stacked(m, clf, langs)
+    ok = sar.LanguageClassifier(input_dim=m.config.d_model, num_classes=2, languages=langs)
+    assert sar.AdapterRouter.from_stacked(m, ok, langs).languages == langs
