@@ -13,7 +13,13 @@ with random-init weights; the LoRA linear is oracle.lora (PEFT's formula).  Inst
 Whisper this oracle keeps one copy whose LoRA modules switch adapter per utterance — arithmetically identical to
 the reference's separate copies, because the base weights are shared and frozen.
 
-PARITY UNPINNED by the reference: it ships no forward-pass numbers.
+PINNED against the reference run here: tests/golden/make_routed_golden.py loads the reference's unmodified
+``AdapterRouter`` / ``EncoderFeatureExtractor`` / ``LanguageClassifier`` by file path, gives them the installed HF
+Whisper as ``base_model`` and one full model copy per language (PEFT's formula at q_proj / v_proj) as ``adapters``, and
+records forward (hard / soft / threshold, loss aggregation), detect_language and generate (EOS handling, zero
+right-padding, ``language=``) — tests/golden/routed_forward_golden.pt.  tests/test_oracle_cpu.py checks that this
+restatement reproduces those outputs bit for bit.  What stays unpinned is only PEFT's ``lora.Linear`` arithmetic itself
+(``peft`` is neither vendored nor installable offline; oracle/lora.py restates its published formula).
 """
 from __future__ import annotations
 
@@ -38,6 +44,10 @@ GEOMETRY = {  # d_model, layers, heads, ffn, mel bins, vocab
     "small": (768, 12, 12, 3072, 80, 51865),
     "medium": (1024, 24, 16, 4096, 80, 51865),
     "large-v3": (1280, 32, 20, 5120, 128, 51866),
+    # two-layer cuts of the medium / large-v3 geometries (same d_model, heads, ffn, mel bins, vocabulary): every kernel
+    # shape of BASELINE configs 3 / 4 at a depth the fp32 CPU oracle finishes in seconds
+    "medium-2l": (1024, 2, 16, 4096, 80, 51865),
+    "large-v3-2l": (1280, 2, 20, 5120, 128, 51866),
 }
 
 
@@ -162,10 +172,12 @@ class RoutedWhisperOracle:
         return out["probs"].argmax(-1), out, h
 
     @torch.no_grad()
-    def forward_hard(self, input_features: torch.Tensor, decoder_input_ids: torch.Tensor,
+    def forward_hard(self, input_features: torch.Tensor, decoder_input_ids: Optional[torch.Tensor],
                      labels: Optional[torch.Tensor] = None, idx: Optional[torch.Tensor] = None,
                      capture: bool = False):
-        """Per-utterance batch-1 loop (adapter_router.py:610-622).  Returns dict(logits, loss, idx[, captured])."""
+        """Per-utterance batch-1 loop (adapter_router.py:610-622).  Returns dict(logits, loss, idx[, captured]).
+        ``decoder_input_ids=None`` with labels: HF builds them from the labels (shift right), as when the reference is
+        called with labels only."""
         if idx is None:
             idx, _, _ = self.detect(input_features)
         logits, losses = [], []
@@ -175,11 +187,15 @@ class RoutedWhisperOracle:
             if capture:
                 for p, m in self.mods.items():
                     m.capture = []
-            out = self.model(input_features=input_features[i:i + 1], decoder_input_ids=decoder_input_ids[i:i + 1])
+            if decoder_input_ids is None:
+                out = self.model(input_features=input_features[i:i + 1], labels=labels[i:i + 1])
+                losses.append(out.loss)
+            else:
+                out = self.model(input_features=input_features[i:i + 1], decoder_input_ids=decoder_input_ids[i:i + 1])
+                if labels is not None:
+                    V = out.logits.shape[-1]
+                    losses.append(F.cross_entropy(out.logits.reshape(-1, V), labels[i].reshape(-1), ignore_index=-100))
             logits.append(out.logits)
-            if labels is not None:
-                V = out.logits.shape[-1]
-                losses.append(F.cross_entropy(out.logits.reshape(-1, V), labels[i].reshape(-1), ignore_index=-100))
             if capture:
                 for p, m in self.mods.items():
                     cap[p].append(m.capture[0])
@@ -191,16 +207,53 @@ class RoutedWhisperOracle:
         return res
 
     @torch.no_grad()
+    def forward_soft(self, input_features: torch.Tensor, labels: Optional[torch.Tensor] = None,
+                     decoder_input_ids: Optional[torch.Tensor] = None, probs: Optional[torch.Tensor] = None):
+        """Every adapter on the WHOLE batch, logits mixed by LID probability; loss = Σ_k mean_b(p[b,k]) · loss_k with
+        loss_k HF's batch token-mean (adapter_router.py:627-670)."""
+        if probs is None:
+            _, out, _ = self.detect(input_features)
+            probs = out["probs"]
+        weighted, loss = None, None
+        for k in range(probs.shape[1]):
+            self._select(k)
+            o = self.model(input_features=input_features, labels=labels, decoder_input_ids=decoder_input_ids)
+            term = probs[:, k:k + 1, None] * o.logits
+            weighted = term if weighted is None else weighted + term
+            if labels is not None:
+                l = probs[:, k].mean() * o.loss
+                loss = l if loss is None else loss + l
+        return {"logits": weighted, "loss": loss, "probs": probs}
+
+    @torch.no_grad()
+    def forward_threshold(self, input_features: torch.Tensor, threshold: float, labels: Optional[torch.Tensor] = None,
+                          decoder_input_ids: Optional[torch.Tensor] = None):
+        """Hard when every utterance's top probability exceeds the threshold, else soft (adapter_router.py:672-693: the
+        mixed case also falls back to soft)."""
+        idx, out, _ = self.detect(input_features)
+        if bool((out["probs"].max(dim=-1).values > threshold).all()):
+            r = self.forward_hard(input_features, decoder_input_ids, labels, idx=idx)
+            return {"logits": r["logits"], "loss": r["loss"]}
+        return self.forward_soft(input_features, labels, decoder_input_ids, probs=out["probs"])
+
+    @torch.no_grad()
+    def generate_language(self, input_features: torch.Tensor, k: int, **kwargs) -> torch.Tensor:
+        """``generate(language=...)``: the named adapter's batched generate, returned unchanged (adapter_router.py:735-738)."""
+        self._select(k)
+        return self.model.generate(input_features=input_features, **kwargs)
+
+    @torch.no_grad()
     def generate_hard(self, input_features: torch.Tensor, max_new_tokens: int = 16,
-                      idx: Optional[torch.Tensor] = None) -> torch.Tensor:
-        """Per-utterance greedy generate, right-padded with 0 (adapter_router.py:744-761)."""
+                      idx: Optional[torch.Tensor] = None, **kwargs) -> torch.Tensor:
+        """Per-utterance greedy generate, right-padded with 0 (adapter_router.py:744-761).  HF's Whisper ``generate``
+        returns the NEW tokens without the closing EOS, so a finished row is its tokens before EOS, then zeros."""
         if idx is None:
             idx, _, _ = self.detect(input_features)
         outs = []
         for i in range(input_features.shape[0]):
             self._select(int(idx[i]))
             outs.append(self.model.generate(input_features=input_features[i:i + 1], max_new_tokens=max_new_tokens,
-                                            num_beams=1, do_sample=False))
+                                            num_beams=1, do_sample=False, **kwargs))
         L = max(o.shape[1] for o in outs)
         outs = [torch.cat([o, torch.zeros(1, L - o.shape[1], dtype=o.dtype)], 1) if o.shape[1] < L else o
                 for o in outs]

@@ -491,13 +491,13 @@ class AdapterRouter(nn.Module):
         native = greedy_decoder_for(self.whisper)
         plan = plan_greedy(self.whisper, input_features, kwargs) if native.supported() else None
         if plan is not None:
-            # one CUDA-graph'd token step for the whole mixed-language batch (decode.py)
+            # one CUDA-graph'd token step for the whole mixed-language batch (decode.py); rows keep their EOS, then pad
             ids = native.generate(input_features, plan, idx)
             if language is not None:
-                # reference :735-738 returns adapter.generate() unchanged: finished rows stay padded with HF's
-                # pad_token_id (a special token that batch_decode strips), NOT with 0 ('!')
-                return ids
-            return _zero_pad_after_eos(ids, plan.eos_ids, first_is_prompt=False)
+                # reference :735-738 returns the adapter's batched HF generate unchanged: HF drops each row's closing EOS
+                # and right-pads with pad_token_id (generation_whisper.py "remove eos token")
+                return _cut_at_first_stop(ids, plan.eos_ids, fill=plan.pad_id)
+            return _cut_at_first_stop(ids, plan.eos_ids, fill=0)
         was_ckpt = self.whisper.model.encoder.gradient_checkpointing
         if was_ckpt:
             self.whisper.gradient_checkpointing_disable()
@@ -512,21 +512,27 @@ class AdapterRouter(nn.Module):
                 self.whisper.gradient_checkpointing_enable()
         if language is not None:
             return ids
-        return _zero_pad_after_eos(ids, self.whisper.generation_config.eos_token_id)
+        # HF's batched output: each row's tokens before its EOS, right-padded with pad_token_id -> zeros instead
+        gc = self.whisper.generation_config
+        stops = []
+        for v in (kwargs.get("eos_token_id", gc.eos_token_id), kwargs.get("pad_token_id", gc.pad_token_id)):
+            if v is not None:
+                stops += list(v) if isinstance(v, (list, tuple)) else [v]
+        return _cut_at_first_stop(ids, stops, fill=0)
 
 
-def _zero_pad_after_eos(ids: torch.Tensor, eos_token_id, first_is_prompt: bool = False) -> torch.Tensor:
-    """Per-sample generation stops at the first EOS (kept); the reference then right-pads with 0 (:753-761).
-    HF's Whisper ``generate`` returns the NEW tokens only, so every position may hold a genuine EOS."""
-    if eos_token_id is None or (isinstance(eos_token_id, (list, tuple)) and not eos_token_id):
+def _cut_at_first_stop(ids: torch.Tensor, stop_ids, fill: int = 0) -> torch.Tensor:
+    """What the reference's per-sample loop returns (:744-761): HF's Whisper ``generate`` yields the NEW tokens of one clip
+    WITHOUT its closing EOS, and shorter rows are right-padded (with 0 by the reference's loop, with pad_token_id by HF's
+    own batched call).  ``ids``: [B, L] rows holding tokens, then a stop token (EOS), then anything.  Every position from
+    a row's first stop token on becomes ``fill``; the width is the longest row's length before its stop token."""
+    if stop_ids is None or (isinstance(stop_ids, (list, tuple)) and not stop_ids) or ids.numel() == 0:
         return ids
-    eos_ids = eos_token_id if isinstance(eos_token_id, (list, tuple)) else [eos_token_id]
-    is_eos = torch.zeros_like(ids, dtype=torch.bool)
-    for e in eos_ids:
-        is_eos |= ids == e
-    if first_is_prompt:
-        is_eos[:, 0] = False
-    after = (is_eos.cumsum(dim=1) - is_eos.long()) > 0   # strictly after the first EOS
-    out = ids.masked_fill(after, 0)
-    lengths = (~after).sum(dim=1)
+    stop_ids = stop_ids if isinstance(stop_ids, (list, tuple)) else [stop_ids]
+    is_stop = torch.zeros_like(ids, dtype=torch.bool)
+    for e in stop_ids:
+        is_stop |= ids == e
+    dead = is_stop.cumsum(dim=1) > 0                    # at or after the first stop token
+    out = ids.masked_fill(dead, fill)
+    lengths = (~dead).sum(dim=1)
     return out[:, : int(lengths.max().item())]

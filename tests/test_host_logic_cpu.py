@@ -175,13 +175,25 @@ def test_per_utterance_loss_is_mean_of_per_sample_means():
     assert torch.allclose(lid_router._per_utterance_loss(logits, labels), want, atol=1e-6)
 
 
-def test_zero_pad_after_eos_matches_per_sample_generate_padding():
+def test_cut_at_first_stop_matches_the_reference_runs_generate_padding():
+    """Pinned by tests/golden/routed_forward_golden.pt ("generate_eos"): HF's Whisper generate drops a row's closing EOS,
+    the reference's loop pads shorter rows with 0 (adapter_router.py:753-761)."""
     eos = 3
     ids = torch.tensor([[4, 9, 8, 3, 1, 1], [4, 7, 3, 1, 1, 1], [4, 5, 6, 7, 8, 9]])
-    out = lid_router._zero_pad_after_eos(ids, eos)
-    assert out.tolist() == [[4, 9, 8, 3, 0, 0], [4, 7, 3, 0, 0, 0], [4, 5, 6, 7, 8, 9]]
+    out = lid_router._cut_at_first_stop(ids, [eos], fill=0)
+    assert out.tolist() == [[4, 9, 8, 0, 0, 0], [4, 7, 0, 0, 0, 0], [4, 5, 6, 7, 8, 9]]
     ids = torch.tensor([[4, 9, 3, 1], [4, 3, 1, 1]])
-    assert lid_router._zero_pad_after_eos(ids, eos).tolist() == [[4, 9, 3], [4, 3, 0]]
+    assert lid_router._cut_at_first_stop(ids, eos).tolist() == [[4, 9], [4, 0]]        # width = longest row before EOS
+    assert lid_router._cut_at_first_stop(ids, [eos], fill=1).tolist() == [[4, 9], [4, 1]]  # generate(language=): HF's pad
+    assert lid_router._cut_at_first_stop(ids, None) is ids
+    # the golden's own EOS case, replayed on the raw (EOS kept, then pad) rows a batched decoder produces
+    from golden_cases import load_golden
+    rec = load_golden()["cases"][0]
+    e, free = rec["generate_eos"], rec["generate"]["ids"]
+    raw = free.clone()
+    hit = (raw == e["eos_token_id"]).cumsum(1) > 1          # after the first EOS: anything (here: pad id 1)
+    raw[hit] = 1
+    assert torch.equal(lid_router._cut_at_first_stop(raw, [e["eos_token_id"]], fill=0), e["ids"])
 
 
 def test_whisper_lora_wrapper_api_offline(monkeypatch):

@@ -220,3 +220,67 @@ def test_lora_oracle_agrees_with_an_independent_multi_lora_restatement():
     y = torch.nn.functional.linear(flat, W, b).clone()
     vops.sgmv_expand(u, Bm, y, start, seq_len, idx, Bsz, T, Bsz * T, add_inputs=True)
     assert torch.allclose(y.view(Bsz, T, -1), want, atol=1e-5, rtol=1e-5)
+
+
+def _same(a, b, exact):
+    """bit-for-bit on the machine class the golden was generated on; 1e-5 of the largest value elsewhere (fp32 GEMM
+    summation order depends on the thread count and the CPU's vector ISA)."""
+    if exact:
+        return torch.equal(a, b)
+    return bool((a - b).abs().max() <= 1e-5 * b.abs().max().clamp_min(1e-12))
+
+
+def test_routed_oracle_reproduces_the_reference_adapter_router_outputs():
+    """oracle/whisper.py vs tests/golden/routed_forward_golden.pt — outputs of the reference's UNMODIFIED AdapterRouter
+    (src/models/adapter_router.py:488-761) run in the build container: hard / soft / threshold forward with loss
+    aggregation, detect_language, generate with EOS stripping + zero right-padding, generate(language=...)."""
+    from golden_cases import Case, checksum, load_golden
+
+    g = load_golden()
+    exact = (g["threads"] == torch.get_num_threads() and g["cpu_capability"] == torch.backends.cpu.get_cpu_capability()
+             and g["torch"] == str(torch.__version__))
+    for rec in g["cases"]:
+        c = Case(rec)
+        o = c.oracle()
+        idx, det, h = o.detect(c.x)
+        assert torch.equal(idx, rec["idx"])                                   # integer work: always bit-exact
+        assert [rec["languages"][k] for k in idx.tolist()] == rec["names"]
+        assert _same(det["probs"], rec["probs"], exact)
+        assert _same(h[:, 0, :], rec["lid_features_row0"], exact)
+        assert abs(checksum(h) - rec["lid_features_checksum"]) <= 1e-6 * rec["lid_features_checksum"]
+
+        r = o.forward_hard(c.x, None, c.labels)                               # labels only (:610-622, :695-713)
+        assert _same(r["logits"], rec["hard_labels"]["logits"], exact)
+        assert _same(r["loss"], rec["hard_labels"]["loss"], exact)
+        # explicit decoder inputs equal to HF's shift of the labels give the same logits (the reference cannot be called
+        # that way for B > 1: it does not slice **kwargs per utterance, see tests/golden/make_routed_golden.py)
+        from transformers.models.whisper.modeling_whisper import shift_tokens_right
+        dec = shift_tokens_right(c.labels, c.cfg.pad_token_id, c.cfg.decoder_start_token_id)
+        r2 = o.forward_hard(c.x, dec)
+        assert torch.equal(r2["logits"], r["logits"]) and r2["loss"] is None
+
+        s = o.forward_soft(c.x, c.labels)                                     # :627-670
+        assert _same(s["logits"], rec["soft_labels"]["logits"], exact)
+        assert _same(s["loss"], rec["soft_labels"]["loss"], exact)
+        assert _same(s["probs"], rec["soft_labels"]["probs"], exact)
+
+        for key in ("threshold_0p5", "threshold_1m"):                         # :672-693
+            t = o.forward_threshold(c.x, rec[key]["threshold"], c.labels)
+            assert rec[key]["bit_identical"]
+            assert _same(t["logits"], rec[rec[key]["same_as"]]["logits"], exact)
+            assert _same(t["loss"], rec[key]["loss"], exact)
+            assert sorted(k for k, v in t.items() if v is not None) == rec[key]["keys"]
+
+        n = rec["gen_steps"]
+        assert torch.equal(o.generate_hard(c.x, max_new_tokens=n), rec["generate"]["ids"])            # :715-761
+        if "generate_eos" in rec:
+            e = rec["generate_eos"]
+            ids = o.generate_hard(c.x, max_new_tokens=n, eos_token_id=e["eos_token_id"])
+            assert torch.equal(ids, e["ids"])
+            assert (ids == e["eos_token_id"]).sum() == 0 and (ids == 0).any()   # EOS stripped by HF, zeros after
+        k = rec["languages"].index(rec["generate_language"]["language"])
+        kw = dict(max_new_tokens=n, num_beams=1, do_sample=False)
+        assert torch.equal(o.generate_language(c.x, k, **kw), rec["generate_language"]["ids"])
+        if "generate_language_eos" in rec:
+            e = rec["generate_language_eos"]
+            assert torch.equal(o.generate_language(c.x, k, eos_token_id=e["eos_token_id"], **kw), e["ids"])

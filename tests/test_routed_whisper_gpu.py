@@ -5,7 +5,12 @@ Gates (north star): router adapter indices BIT-EXACT; every LoRA'd module output
 stated bf16 tolerance of the fp32 oracle; identical greedy token sequences on the check set.
 
 Tolerances: the GPU path stores activations in bf16 (2^-8 relative rounding per op) through 2·L layers, the oracle
-is fp32 end to end.  Per LoRA'd module output: max|err| <= 4e-2 * max|ref|; logits: max|err| <= 5e-2 * max|ref|.
+is fp32 end to end.  Per LoRA'd module output and logits: max|err| <= 3e-2 * max|ref|.
+
+Greedy tokens: a row must equal the fp32 reference tokens at every position before the first one whose reference
+top-1 / top-2 logit margin is below MARGIN_EPS (there the argmax of a bf16 path is legitimately ambiguous, and every
+later token depends on it); rows without such a position must be identical over their whole length.  No allowance
+for "most rows".
 """
 import copy
 from pathlib import Path
@@ -18,8 +23,9 @@ from oracle import fixtures, lora as olora, router as orouter, whisper as owhisp
 
 pytestmark = pytest.mark.gpu
 
-MODULE_TOL = 4e-2
-LOGIT_TOL = 5e-2
+MODULE_TOL = 3e-2
+LOGIT_TOL = 3e-2
+MARGIN_EPS = 2e-2     # in units of max|logit| of the row's reference logits (bf16 logits carry ~2^-8 relative noise)
 
 
 def rel_err(y, ref):
@@ -146,34 +152,47 @@ def test_soft_routing_matches_reference_semantics(micro):
     assert rel_err(out["logits"], want) <= LOGIT_TOL
 
 
+def assert_greedy_rows(got, want, margins, absmax):
+    """Row-by-row greedy gate (module docstring).  margins [B, L]: reference top-2 margins, teacher-forced on ``want``."""
+    got, want = got.cpu(), want.cpu()
+    assert got.shape[0] == want.shape[0]
+    n_full = 0
+    for i in range(want.shape[0]):
+        L = want.shape[1]
+        low = (margins[i, :L] < MARGIN_EPS * absmax).nonzero()
+        n_ok = int(low[0]) if len(low) else L
+        assert got.shape[1] >= n_ok, (i, got.shape, n_ok)
+        assert torch.equal(got[i, :n_ok], want[i, :n_ok]), (i, n_ok, got[i].tolist(), want[i].tolist())
+        if n_ok == L:
+            assert got.shape[1] == L or bool((got[i, L:] == 0).all())
+            n_full += 1
+    return n_full
+
+
+def oracle_margins(s, x, want, idx):
+    """Reference top-2 margins at every generated position, teacher-forced on the reference's own tokens."""
+    B, L = want.shape
+    m = torch.zeros(B, L)
+    absmax = 0.0
+    start = torch.full((1, 1), s.cfg.decoder_start_token_id)
+    for i in range(B):
+        dec_in = torch.cat([start, want[i:i + 1, :-1]], 1)
+        lg = s.oracle.forward_hard(x[i:i + 1], dec_in, idx=idx[i:i + 1])["logits"][0]
+        m[i] = orouter.top2_margin(lg)
+        absmax = max(absmax, lg.abs().max().item())
+    return m, absmax
+
+
 def test_greedy_generation_matches_oracle_tokens(micro):
-    """Identical greedy token sequences; a sequence is compared up to (excluding) the first step whose oracle
-    top-1/top-2 logit margin is below the bf16 noise floor, where argmax is legitimately ambiguous."""
     s = micro
-    B, steps = 6, 8
+    B, steps = 8, 32
     x, *_ = s.batch(B, 4, seed=5)
     want = s.oracle.generate_hard(x, max_new_tokens=steps)
     with torch.no_grad():
         got = s.router.generate(x.to(s.dev).to(torch.bfloat16), max_new_tokens=steps, num_beams=1, do_sample=False)
-    got = got.cpu()
-    assert got.shape[0] == B
-    # oracle margins per generated position, teacher-forced on the oracle's own tokens
     idx, _, _ = s.oracle.detect(x)
-    full = 0
-    for i in range(B):
-        L = min(want.shape[1], got.shape[1])
-        seq = want[i:i + 1, :L]
-        start = torch.full((1, 1), s.cfg.decoder_start_token_id)
-        dec_in = torch.cat([start, seq[:, :-1]], 1) if seq[0, 0] != s.cfg.decoder_start_token_id else seq
-        r = s.oracle.forward_hard(x[i:i + 1], dec_in, idx=idx[i:i + 1])
-        margins = orouter.top2_margin(r["logits"][0])
-        n_ok = L
-        low = (margins < 2e-2).nonzero()
-        if len(low):
-            n_ok = int(low[0])
-        assert torch.equal(got[i, :n_ok], want[i, :n_ok]), (i, got[i].tolist(), want[i].tolist())
-        full += int(torch.equal(got[i, :L], want[i, :L]))
-    assert full >= B - 2
+    margins, absmax = oracle_margins(s, x, want, idx)
+    assert_greedy_rows(got, want, margins, absmax)
 
 
 def test_module_default_and_beam_expanded_routing(cuda_dev):
@@ -308,17 +327,8 @@ def test_config1_whisper_small_single_adapter_one_clip(cuda_dev, tmp_path):
     want = s.oracle.generate_hard(x, max_new_tokens=steps)
     with torch.no_grad():
         got = s.router.generate(x.to(s.dev).to(torch.bfloat16), max_new_tokens=steps, num_beams=1, do_sample=False).cpu()
-    L = min(want.shape[1], got.shape[1])
-    start = torch.full((1, 1), s.cfg.decoder_start_token_id)
-    r = s.oracle.forward_hard(x, torch.cat([start, want[:, :L - 1]], 1), idx=torch.zeros(1, dtype=torch.long))
-    lg = r["logits"][0]                                   # oracle logits, teacher-forced on the oracle's own tokens
-    mism = (got[0, :L] != want[0, :L]).nonzero()
-    if len(mism):
-        # random-init whisper-small has nearly flat logits: at the first differing position the GPU's token must be an
-        # argmax of the oracle up to the logit tolerance (an fp32-vs-bf16 tie), and everything before it is identical
-        t = int(mism[0])
-        gap = (lg[t].max() - lg[t, got[0, t]]).item()
-        assert gap <= LOGIT_TOL * lg.abs().max().item(), (t, gap, got.tolist(), want.tolist())
+    margins, absmax = oracle_margins(s, x, want, torch.zeros(1, dtype=torch.long))
+    assert_greedy_rows(got, want, margins, absmax)
     assert got.shape[0] == 1 and got.dtype == torch.long
 
 
@@ -354,3 +364,178 @@ def test_training_forward_backward_with_lora_dropout_matches_pefts_formula(cuda_
     assert rel(y.detach().float(), ref.detach()) <= 2.0 ** -6
     assert rel(gx, xr.grad) <= 2.0 ** -5
     assert rel(gA, A.grad) <= 2.0 ** -5 and rel(gB, Bw.grad) <= 2.0 ** -5
+
+
+# ------------------------------------------------------------------------------------------------ reference-run golden
+class GoldenSetup:
+    """The product's AdapterRouter built on the regenerated inputs of one tests/golden/routed_forward_golden.pt case
+    (outputs of the reference's unmodified AdapterRouter, tests/golden/make_routed_golden.py)."""
+
+    def __init__(self, rec, dev, tmp):
+        from golden_cases import Case
+
+        self.rec, self.dev = rec, dev
+        c = self.c = Case(rec)
+        self.languages = rec["languages"]
+        paths = {}
+        for k, lang in enumerate(self.languages):
+            owhisper.write_peft_adapter(tmp / lang, c.weights, k, rec["r"], 2 * rec["r"])
+            paths[lang] = tmp / lang
+        gpu_model = owhisper.build_whisper(rec["geometry"]).to(torch.bfloat16).to(dev)
+        clf = sar.LanguageClassifier(input_dim=c.cfg.d_model, num_classes=rec["C"], languages=self.languages)
+        clf.load_state_dict(c.router_sd)
+        self.router = sar.AdapterRouter(gpu_model, paths, clf.eval().to(dev), self.languages).eval()
+        self.x = c.x.to(dev).to(torch.bfloat16)
+        self.labels = c.labels.to(dev)
+
+
+@pytest.fixture(scope="module", params=[0, 1])
+def golden(request, cuda_dev, tmp_path_factory):
+    from golden_cases import load_golden
+
+    rec = load_golden()["cases"][request.param]
+    return GoldenSetup(rec, cuda_dev, tmp_path_factory.mktemp(f"golden{request.param}"))
+
+
+def test_reference_run_golden_forward_hard_soft_threshold(golden):
+    """B200 path vs the REFERENCE's own AdapterRouter outputs (fp32 CPU run, committed golden): detected languages
+    bit-exact, logits of every strategy within LOGIT_TOL, losses within 2 %."""
+    s, rec = golden, golden.rec
+    r = s.router
+    with torch.no_grad():
+        h = r.extract_encoder_features(s.x)
+        names, probs = r.detect_language(h)
+        assert names == rec["names"]                                                   # :550-566
+        assert torch.equal(r.detect_indices(h).idx.cpu().long(), rec["idx"])
+        assert (probs.float().cpu() - rec["probs"]).abs().max().item() <= 2e-2
+        assert rel_err(h[:, 0, :], rec["lid_features_row0"]) <= MODULE_TOL
+
+        out = r(s.x, labels=s.labels)                                                  # hard :599-625, :695-713
+        assert set(out) == {"loss", "logits"}
+        assert rel_err(out["logits"], rec["hard_labels"]["logits"]) <= LOGIT_TOL
+        assert abs(out["loss"].item() - rec["hard_labels"]["loss"].item()) <= 2e-2 * rec["hard_labels"]["loss"].item()
+        try:
+            r.strategy = "soft"                                                        # :627-670
+            out = r(s.x, labels=s.labels)
+            assert set(out) == {"loss", "logits", "probs"}
+            assert rel_err(out["logits"], rec["soft_labels"]["logits"]) <= LOGIT_TOL
+            assert abs(out["loss"].item() - rec["soft_labels"]["loss"].item()) <= 2e-2 * rec["soft_labels"]["loss"].item()
+            for key in ("threshold_0p5", "threshold_1m"):                              # :672-693
+                r.strategy, r.threshold = "threshold", rec[key]["threshold"]
+                out = r(s.x, labels=s.labels)
+                assert sorted(k for k, v in out.items() if v is not None) == rec[key]["keys"]
+                assert rel_err(out["logits"], rec[rec[key]["same_as"]]["logits"]) <= LOGIT_TOL
+                assert abs(out["loss"].item() - rec[key]["loss"].item()) <= 2e-2 * rec[key]["loss"].item()
+        finally:
+            r.strategy, r.threshold = "hard", 0.7
+
+
+def test_reference_run_golden_generate(golden):
+    """generate (:715-761) vs the reference run: same tokens (margin gate), EOS dropped and zeros after it, width = the
+    longest row; generate(language=...) = the named adapter's batched HF generate, padded with pad_token_id."""
+    s, rec = golden, golden.rec
+    n = rec["gen_steps"]
+    g = rec["generate"]
+    kw = dict(max_new_tokens=n, num_beams=1, do_sample=False)
+    with torch.no_grad():
+        got = s.router.generate(s.x, **kw)
+        full = assert_greedy_rows(got, g["ids"], g["margins"], g["logit_absmax"])
+        assert got.dtype == torch.long
+        if "generate_eos" in rec:
+            e = rec["generate_eos"]
+            got_e = s.router.generate(s.x, eos_token_id=e["eos_token_id"], **kw).cpu()
+            if full == rec["B"] and torch.equal(got.cpu(), g["ids"]):
+                assert torch.equal(got_e, e["ids"])                                    # incl. the zero right-padding
+            assert (got_e == e["eos_token_id"]).sum() == 0
+        gl = rec["generate_language"]
+        got_l = s.router.generate(s.x, language=gl["language"], **kw).cpu()
+        k = rec["languages"].index(gl["language"])
+        m_l, absmax = oracle_margins(_OracleView(s.c), s.c.x, gl["ids"], torch.full((rec["B"],), k))
+        assert_greedy_rows(got_l, gl["ids"], m_l, absmax)
+        if "generate_language_eos" in rec:
+            e = rec["generate_language_eos"]
+            got_le = s.router.generate(s.x, language=gl["language"], eos_token_id=e["eos_token_id"], **kw).cpu()
+            if torch.equal(got_l, gl["ids"]):
+                assert torch.equal(got_le, e["ids"])
+
+
+class _OracleView:
+    def __init__(self, case):
+        self.cfg = case.cfg
+        self.oracle = case.oracle()
+
+
+# ------------------------------------------------------------------------------------------------ benchmarked geometries
+def _model_level_check(s, B, T_dec, kind, seed):
+    x, dec, labels, langs = s.batch(B, T_dec, kind, seed=seed)
+    ref = s.oracle.forward_hard(x, dec, labels, capture=True)
+    xg = x.to(s.dev).to(torch.bfloat16)
+    captured = {}
+    hooks = [m.register_forward_hook(lambda mod, inp, out, p=p: captured.setdefault(p, []).append(out.detach()))
+             for p, m in sar.lora_modules(s.router.whisper).items()]
+    try:
+        with torch.no_grad():
+            routed = s.router.detect_indices(s.router.extract_encoder_features(xg))
+            captured.clear()
+            out = s.router._hard_routing(xg, routed.idx, labels.to(s.dev))
+    finally:
+        for hk in hooks:
+            hk.remove()
+    assert torch.equal(routed.idx.cpu().long(), ref["idx"]) and ref["idx"].tolist() == langs
+    assert rel_err(out["logits"], ref["logits"]) <= LOGIT_TOL
+    assert abs(out["loss"].item() - ref["loss"].item()) <= 2e-2 * abs(ref["loss"].item())
+    return captured, ref
+
+
+def test_fused_blocks_are_what_the_micro_model_runs(micro):
+    """The model-level fixtures must exercise the benchmarked path: every encoder / decoder layer of the head_dim-64
+    micro geometry is bound to the fused body, and a routed forward launches libsar's projection / dense / LayerNorm /
+    attention kernels for it (not HF's eager bodies over the K1 module slots)."""
+    from speech_adapter_routing_b200 import ops
+
+    w = micro.router.whisper
+    layers = list(w.model.encoder.layers) + list(w.model.decoder.layers)
+    assert all(hasattr(l, "_sar_pack") for l in layers)
+    x, dec, labels, _ = micro.batch(4, 8, seed=21)
+    ops.reset_counters()
+    with torch.no_grad():
+        micro.router(x.to(micro.dev).to(torch.bfloat16), labels=labels.to(micro.dev))
+    n_enc, n_dec = len(w.model.encoder.layers), len(w.model.decoder.layers)
+    assert ops.LAUNCHES["k1"] == 0                                    # no module-slot K1 calls: the layer bodies are fused
+    assert ops.LAUNCHES["ln"] >= 2 * (2 * n_enc + 1) + 3 * n_dec + 1   # LID pass + routed pass
+    assert ops.LAUNCHES["linear"] >= 2 * 3 * n_enc + 4 * n_dec
+    assert ops.LAUNCHES["proj"] >= 2 * n_enc + 3 * n_dec
+    assert ops.LAUNCHES["k2"] == 2
+
+
+def test_whisper_small_mixed_adapter_batch(cuda_dev, tmp_path):
+    """BASELINE config 2's geometry and adapter set (whisper-small, 4 adapters r16), mixed-language batch of 8: routing
+    bit-exact, logits / loss within tolerance of the fp32 oracle, every LoRA'd module output of one encoder and one
+    decoder layer within tolerance."""
+    s = Setup("small", 4, 16, cuda_dev, tmp_path)
+    captured, ref = _model_level_check(s, 8, 16, "uniform", seed=31)
+    for p, want in ref["captured"].items():
+        if ".layers.0." in p or ".layers.11." in p:
+            assert rel_err(captured[p][0], want) <= MODULE_TOL, p
+
+
+@pytest.mark.parametrize("geo,C,r", [("medium-2l", 4, 32), ("large-v3-2l", 8, 64)])
+def test_medium_and_large_v3_geometry_model_level(cuda_dev, tmp_path, geo, C, r):
+    """BASELINE configs 3 / 4 kernel shapes (d = 1024 r32 x4 adapters; d = 1280, 128 mel bins, r64 x8 adapters) on
+    two-layer models against the fp32 oracle: routing bit-exact, every LoRA'd module output and the logits within tolerance."""
+    s = Setup(geo, C, r, cuda_dev, tmp_path)
+    captured, ref = _model_level_check(s, 2 * C if C == 4 else C, 12, "uniform", seed=41)
+    for p, want in ref["captured"].items():
+        assert rel_err(captured[p][0], want) <= MODULE_TOL, p
+
+
+def test_whisper_small_greedy_32_tokens_batch_8(cuda_dev, tmp_path):
+    """SURVEY §8(d) greedy gate at its stated size: whisper-small, B = 8 mixed languages, 32 new tokens."""
+    s = Setup("small", 4, 16, cuda_dev, tmp_path)
+    x, *_ = s.batch(8, 4, "uniform", seed=51)
+    want = s.oracle.generate_hard(x, max_new_tokens=32)
+    with torch.no_grad():
+        got = s.router.generate(x.to(s.dev).to(torch.bfloat16), max_new_tokens=32, num_beams=1, do_sample=False)
+    idx, _, _ = s.oracle.detect(x)
+    margins, absmax = oracle_margins(s, x, want, idx)
+    assert_greedy_rows(got, want, margins, absmax)
