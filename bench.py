@@ -11,11 +11,21 @@ Workload at every N: BASELINE.json configs[1] — whisper-small geometry, 4 lang
 batch 64 *per GPU* (weak scaling: utterances are independent, batch sharded, adapters replicated, no data-path
 collective).  Weights are random-init (no hub access), inputs synthetic.
 
+Beside the headline the line carries bounded extra legs under ``"extra"`` (``--extras none`` skips them):
+  medium / large_v3   BASELINE configs[2] / [3] per-GPU shards (whisper-medium 4 x r32, whisper-large-v3 8 x r64, 64 clips
+                      per GPU), a few steps each, with their own q|k|v+LoRA roofline;
+  train               BASELINE configs[4]: whisper-small LoRA r16 training step (fwd + LoRA-only bwd through K3, bf16 base,
+                      gradient checkpointing as in WhisperLoRA's default), 16 clips per GPU, NCCL all-reduce of the flat
+                      fp32 adapter-gradient bucket at N > 1 with its own time and bytes;
+  gpu_eager_baseline  (N = 1) the reference's per-utterance loop — HF Whisper + eager PEFT-formula LoRA — in bf16 on the
+                      SAME B200 (oracle port moved to the GPU), on a bounded sample: what the kernels buy over torch eager.
+
 Prints ONE JSON line on rank 0.
 """
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -30,21 +40,36 @@ sys.path.insert(0, str(ROOT))
 
 METRIC = "routed_multi_lora_whisper_fwd_clips_per_sec"
 UNIT = "clips/s"
-WORKLOAD = "whisper-small routed fwd: 4 adapters r16 on q_proj/v_proj, LID pass + router + routed enc/dec pass, T_dec=128"
-MODEL, N_ADAPTERS, RANK_R, BATCH_PER_GPU, T_DEC = "whisper-small", 4, 16, 64, 128
-LANGUAGES = ["hindi", "italian", "punjabi", "telugu"]
+T_DEC = 128
 ALL_LANGUAGES = ["hindi", "italian", "punjabi", "telugu", "english", "german", "french", "spanish"]
 
 
-def configure(model: str, adapters: int, rank: int, batch: int) -> None:
-    """Non-default workloads (BASELINE configs 3 / 4: whisper-medium r32, whisper-large-v3 8 adapters r64) for
-    profiling runs; the driver's bench line always uses the defaults (config 2, the one the metric is quoted on)."""
-    global WORKLOAD, MODEL, N_ADAPTERS, RANK_R, BATCH_PER_GPU, LANGUAGES
-    MODEL, N_ADAPTERS, RANK_R, BATCH_PER_GPU = model, adapters, rank, batch
-    LANGUAGES = ALL_LANGUAGES[:adapters]
-    WORKLOAD = (f"{model} routed fwd: {adapters} adapters r{rank} on q_proj/v_proj, LID pass + router + routed enc/dec "
-                f"pass, T_dec={T_DEC}")
+class Workload:
+    """One routed-forward configuration (BASELINE.json configs[1..3])."""
+
+    def __init__(self, model: str, adapters: int, rank: int, batch: int):
+        self.model, self.adapters, self.rank, self.batch = model, adapters, rank, batch
+        self.languages = ALL_LANGUAGES[:adapters]
+        self.name = (f"{model} routed fwd: {adapters} adapters r{rank} on q_proj/v_proj, LID pass + router + routed "
+                     f"enc/dec pass, T_dec={T_DEC}")
+
+
+HEADLINE = Workload("whisper-small", 4, 16, 64)            # configs[1]: the configuration the metric is quoted on
+EXTRA_WORKLOADS = {"medium": Workload("whisper-medium", 4, 32, 64),       # configs[2]: 256 clips over 4 GPUs
+                   "large_v3": Workload("whisper-large-v3", 8, 64, 64)}   # configs[3]: 512 clips over 8 GPUs
 FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE launch of the roofline kernel (k1v2<256,AUG>: the dense q|k|v launch
+# with the low-rank term as one extra K block, M = 96000, 768 -> 2304, r = 16), from the `ncu --set full` capture of THIS
+# build summarised in profiles/r02_qkv_lora_ncu_full_summary.csv (tools/profile_all.sh regenerates it).  Algorithmic bytes
+# of that launch: x 147.5 + y 442.4 + W 3.5 + U 6.1 + adapters 0.1 = 599.6 MB.  None until the capture exists.
+K1_DRAM_TRAFFIC = {"bytes": None, "source": None}
+_traffic_file = ROOT / "profiles" / "r02_qkv_lora_traffic.json"
+if _traffic_file.exists():
+    try:
+        K1_DRAM_TRAFFIC = json.loads(_traffic_file.read_text())
+    except Exception:
+        pass
 
 
 def load_peaks():
@@ -112,6 +137,37 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------- reference arm
+def build_oracle_workload(sample_B: int, wl: Workload = HEADLINE, device: str = "cpu", dtype=None):
+    import torch
+
+    from oracle import fixtures, whisper as owhisper
+
+    geo = wl.model.replace("whisper-", "")
+    model = owhisper.build_whisper(geo)
+    cfg = model.config
+    weights = owhisper.make_adapter_weights(model, wl.rank, wl.adapters)
+    sd = fixtures.make_router_state_dict(cfg.d_model, wl.adapters)
+    if dtype is not None:
+        model = model.to(dtype)
+        weights = {k: (A.to(dtype), B.to(dtype)) for k, (A, B) in weights.items()}
+    if device != "cpu":
+        model = model.to(device)
+        weights = {k: (A.to(device), B.to(device)) for k, (A, B) in weights.items()}
+        sd = {k: v.to(device) for k, v in sd.items()}
+    oracle = owhisper.RoutedWhisperOracle(model, weights, wl.rank, 2 * wl.rank, sd)
+    protos = owhisper.make_input_features(wl.adapters, cfg.num_mel_bins, list(range(wl.adapters)), wl.adapters, seed=99)
+    langs = fixtures.language_mix(sample_B, wl.adapters, "uniform")
+    x = owhisper.make_input_features(sample_B, cfg.num_mel_bins, langs, wl.adapters)
+    dec, _ = owhisper.make_decoder_inputs(sample_B, T_DEC, cfg.vocab_size, cfg.decoder_start_token_id)
+    if device != "cpu" or dtype is not None:
+        protos, x = protos.to(device, dtype or protos.dtype), x.to(device, dtype or x.dtype)
+        dec = dec.to(device)
+    feats = oracle.lid_features(protos)
+    oracle.router_sd = {k: v.to(feats.device) for k, v in owhisper.fit_router_head(
+        {k: v.float().cpu() for k, v in sd.items()}, feats.float().cpu()).items()}
+    return oracle, x, dec
+
+
 def run_reference_arm(args):
     """The reference's own CPU path (HF Whisper fp32 + PEFT-formula LoRA + per-utterance hard-routing loop —
     oracle/, since the reference has no native code to compile and `peft` is not installable offline), all host
@@ -120,8 +176,6 @@ def run_reference_arm(args):
     if rank != 0:
         return
     import torch
-
-    from oracle import fixtures, whisper as owhisper
 
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
@@ -140,7 +194,7 @@ def run_reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps_ref, "warmup": args.warmup_ref, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "sample_batch": sample_B, "device": "cpu"},
+        "config": {"workload": HEADLINE.name, "sample_batch": sample_B, "device": "cpu"},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
                          "sample": f"{sample_B} clips per step (LID encoder pass + per-utterance routed forward), "
                                    f"median of {args.steps_ref} steps; oracle port of the reference path "
@@ -149,24 +203,6 @@ def run_reference_arm(args):
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
-
-
-def build_oracle_workload(sample_B: int):
-    import torch
-
-    from oracle import fixtures, whisper as owhisper
-
-    model = owhisper.build_whisper("small")
-    cfg = model.config
-    weights = owhisper.make_adapter_weights(model, RANK_R, N_ADAPTERS)
-    sd = fixtures.make_router_state_dict(cfg.d_model, N_ADAPTERS)
-    oracle = owhisper.RoutedWhisperOracle(model, weights, RANK_R, 2 * RANK_R, sd)
-    protos = owhisper.make_input_features(N_ADAPTERS, cfg.num_mel_bins, list(range(N_ADAPTERS)), N_ADAPTERS, seed=99)
-    oracle.router_sd = owhisper.fit_router_head(sd, oracle.lid_features(protos))
-    langs = fixtures.language_mix(sample_B, N_ADAPTERS, "uniform")
-    x = owhisper.make_input_features(sample_B, cfg.num_mel_bins, langs, N_ADAPTERS)
-    dec, _ = owhisper.make_decoder_inputs(sample_B, T_DEC, cfg.vocab_size, cfg.decoder_start_token_id)
-    return oracle, x, dec
 
 
 def cpu_baseline(max_seconds: float = 30.0):
@@ -193,11 +229,35 @@ def cpu_baseline(max_seconds: float = 30.0):
             "sample": f"{sample_B} clips per run (LID pass + per-utterance routed fwd, fp32), median of {len(times)} runs"}
 
 
+def gpu_eager_baseline(dev, sample_B: int = 4):
+    """The reference's path as torch would run it on THIS GPU: HF Whisper in bf16 (the reference's CUDA dtype policy,
+    src/models/base.py:103-109) + eager PEFT-formula LoRA + the per-utterance batch-1 loop of adapter_router.py:610-622
+    (the oracle port, moved to the device).  Bounded sample; informational — it is what the libsar kernels replace."""
+    import torch
+
+    oracle, x, dec = build_oracle_workload(sample_B, device=str(dev), dtype=torch.bfloat16)
+    with torch.no_grad():
+        oracle.forward_hard(x[:1], dec[:1])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(2):
+            oracle.forward_hard(x, dec)
+        e1.record()
+        torch.cuda.synchronize()
+    sec = e0.elapsed_time(e1) * 1e-3 / 2
+    del oracle
+    gc.collect()
+    torch.cuda.empty_cache()
+    return {"value": sample_B / sec, "unit": UNIT, "kind": "port", "device": "cuda (same B200)", "dtype": "bf16",
+            "sample": f"{sample_B} clips per run: LID encoder pass + per-utterance batch-1 routed forward, HF eager layers + "
+                      "eager LoRA (torch / cuBLAS / cuDNN kernels), mean of 2 runs"}
+
+
 # --------------------------------------------------------------------------------------------- B200 arm
 def fit_head_gpu(clf, feats):
     """Closed-form nearest-centroid output layer so the synthetic languages route to distinct adapters."""
     import torch
-    import torch.nn.functional as F
 
     with torch.no_grad():
         f = clf.layer_norm(feats.float()).mean(1)
@@ -213,111 +273,74 @@ def fit_head_gpu(clf, feats):
         clf.classifier[-1].bias.copy_(-(w @ z.mean(0)))
 
 
-def build_b200_workload(dev, seed):
+def build_b200_workload(wl: Workload, dev, seed):
     import torch
 
     import speech_adapter_routing_b200 as sar
 
-    model = sar.load_base_model(MODEL, device=dev, random_init=True)     # bf16 on CUDA (reference dtype policy)
+    model = sar.load_base_model(wl.model, device=dev, random_init=True)     # bf16 on CUDA (reference dtype policy)
     cfg = model.config
     for p in model.parameters():
         p.requires_grad = False
-    lcfg = sar.LoraConfig(r=RANK_R, lora_alpha=2 * RANK_R, lora_dropout=0.0, target_modules=["q_proj", "v_proj"])
-    for lang in LANGUAGES:
+    lcfg = sar.LoraConfig(r=wl.rank, lora_alpha=2 * wl.rank, lora_dropout=0.0, target_modules=["q_proj", "v_proj"])
+    for lang in wl.languages:
         sar.inject_lora(model, lcfg, adapter_name=lang)
     g = torch.Generator(device="cpu").manual_seed(seed)
     with torch.no_grad():
         for m in sar.lora_modules(model).values():
-            for lang in LANGUAGES:   # PEFT's zero-init lora_B would make the adapter path a no-op numerically
-                m.lora_B[lang].weight.copy_((torch.randn(m.out_features, RANK_R, generator=g) * 0.02).to(dev))
-    clf = sar.LanguageClassifier(input_dim=cfg.d_model, num_classes=N_ADAPTERS, languages=LANGUAGES).to(dev).eval()
-    router = sar.AdapterRouter.from_stacked(model, clf, LANGUAGES, strategy="hard").eval()
+            for lang in wl.languages:   # PEFT's zero-init lora_B would make the adapter path a no-op numerically
+                m.lora_B[lang].weight.copy_((torch.randn(m.out_features, wl.rank, generator=g) * 0.02).to(dev))
+    clf = sar.LanguageClassifier(input_dim=cfg.d_model, num_classes=wl.adapters, languages=wl.languages).to(dev).eval()
+    router = sar.AdapterRouter.from_stacked(model, clf, wl.languages, strategy="hard").eval()
 
     gt = torch.Generator().manual_seed(4234)
-    templates = torch.rand(N_ADAPTERS, cfg.num_mel_bins, generator=gt) * 2 - 1
+    templates = torch.rand(wl.adapters, cfg.num_mel_bins, generator=gt) * 2 - 1
 
     def clips(B, langs, gen):
         return 0.5 * torch.randn(B, cfg.num_mel_bins, 3000, generator=gen) + templates[torch.tensor(langs)][:, :, None]
 
-    protos = clips(N_ADAPTERS, list(range(N_ADAPTERS)), g).to(dev).to(torch.bfloat16)
+    protos = clips(wl.adapters, list(range(wl.adapters)), g).to(dev).to(torch.bfloat16)
     with torch.no_grad():
         fit_head_gpu(clf, router.extract_encoder_features(protos))
     return router, cfg, clips, g
 
 
-def run_b200_arm(args):
-    import torch
-    import torch.distributed as dist
+class Dist:
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
 
-    from speech_adapter_routing_b200 import _lib, ops
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local_rank)
+        self.dev = torch.device("cuda", self.local_rank)
+        self.dist = dist
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py needs a B200: the product path has no CPU fallback")
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    if _lib.lib().sar_device_ok() != 1:
-        raise SystemExit("libsar: device is not sm_100")
+    def barrier(self):
+        import torch
 
-    router, cfg, clips, g = build_b200_workload(dev, seed=1234 + rank)
-    B = BATCH_PER_GPU
-    n_in = 3   # rotate input buffers; every activation tensor (B*1500*768*2 B = 147 MB) already exceeds the 126 MB L2
-    langs = [[(i + j) % N_ADAPTERS for i in range(B)] for j in range(n_in)]
-    host_inputs = [clips(B, langs[j], g).pin_memory() for j in range(n_in)]          # fp32, as a data loader yields
-    dev_inputs = [h.to(dev).to(torch.bfloat16) for h in host_inputs]
-    dec = torch.randint(5, cfg.vocab_size, (B, T_DEC), generator=g)
-    dec[:, 0] = cfg.decoder_start_token_id
-    dec_dev = dec.to(dev)
-
-    def step(x):
-        with torch.no_grad():
-            return router(x, decoder_input_ids=dec_dev)["logits"]
-
-    def barrier():
         torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
+        if self.world > 1:
+            self.dist.barrier()
             torch.cuda.synchronize()
 
-    # ---- device-resident timing -------------------------------------------------------------------------
-    for i in range(args.warmup):
-        step(dev_inputs[i % n_in])
-    barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    ops.reset_counters()
-    ops.K1_TIMELINE = []
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    t_wall0 = time.time()
-    torch.cuda.nvtx.range_push("timed")
-    e0.record()
-    for i in range(args.steps):
-        out = step(dev_inputs[i % n_in])
-    e1.record()
-    barrier()
-    torch.cuda.nvtx.range_pop()
-    t_wall1 = time.time()
-    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
-    timeline, ops.K1_TIMELINE = ops.K1_TIMELINE, None
-    launches = sum(ops.LAUNCHES.values())
-    ms_total = e0.elapsed_time(e1)
-    t = torch.tensor([ms_total], device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_step = t.item() / args.steps
-    value = world * B / (ms_step * 1e-3)
+    def max_ms(self, ms: float) -> float:
+        import torch
 
-    # ---- roofline of the dominant kernel: the tcgen05 pair kernel at the fused q|k|v + routed-LoRA call of the routed
-    # pass's encoder layers (M = B*1500 rows, N = 3d), timed by CUDA events around every launch inside the timed region
-    peaks, peak_src = load_peaks()
-    M_big = B * 1500
-    d = cfg.d_model
-    fl, ms_k1, n_big = 0.0, 0.0, 0
+        t = torch.tensor([ms], device=self.dev)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return t.item()
+
+
+def qkv_roofline(timeline, M_big, d, rank_r, ms_total, peaks, peak_src):
+    """Roofline of the dominant kernel from the per-launch CUDA events of the timed region: the tcgen05 pair kernel at
+    the fused q|k|v + routed-LoRA call of the routed pass's encoder layers (M = B*1500 rows, N = 3d)."""
+    fl, ms_k1, n_big, ms_gemm_all = 0.0, 0.0, 0, 0.0
     by_kind = {}
-    ms_gemm_all = 0.0
     for (kind, M, d_in, d_out, flops, a, b) in timeline:
         dt = a.elapsed_time(b)
         ms_gemm_all += dt
@@ -331,38 +354,243 @@ def run_b200_arm(args):
             n_big += 1
     achieved = fl / (ms_k1 * 1e-3) / 1e12 if ms_k1 > 0 else 0.0
     peak = float(peaks.get("bf16_tflops_sustained", FALLBACK_PEAKS["bf16_tflops_sustained"]))
-    default_shape = (MODEL, RANK_R, B) == ("whisper-small", 16, 64)
-    roofline = {"bound": "tensor", "kernel": "sar_attn_proj_fwd q|k|v + routed LoRA (M=%d, %d->%d, r=%d): k1v2 U pass + k1v2<256,AUG> dense tiles" % (M_big, d, 3 * d, RANK_R),
-                "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
-                "traffic": K1_DRAM_TRAFFIC_BYTES if default_shape else None, "peak_source": peak_src + ", sustained bf16 (kernel timed inside a long step)",
-                "launches_timed": n_big, "avg_launch_us": 1e3 * ms_k1 / max(n_big, 1),
-                "gemm_share_of_step": ms_gemm_all / ms_total if ms_total else None,
-                "algorithmic_flops_per_launch": fl / max(n_big, 1),
-                "all_tcgen05_gemms": {k: {"launches": v[0], "avg_us": 1e3 * v[1] / v[0], "tflops": v[2] / (v[1] * 1e-3) / 1e12}
-                                      for k, v in sorted(by_kind.items(), key=lambda kv: -kv[1][1])[:20]}}
+    return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None,
+            "peak_source": peak_src + ", sustained bf16 (kernel timed inside a long step)",
+            "frac_of_burst_peak": achieved / float(peaks.get("bf16_tflops", FALLBACK_PEAKS["bf16_tflops"])),
+            "launches_timed": n_big, "avg_launch_us": 1e3 * ms_k1 / max(n_big, 1),
+            "gemm_share_of_step": ms_gemm_all / ms_total if ms_total else None,
+            "algorithmic_flops_per_launch": fl / max(n_big, 1),
+            "all_tcgen05_gemms": {k: {"launches": v[0], "avg_us": 1e3 * v[1] / v[0], "tflops": v[2] / (v[1] * 1e-3) / 1e12}
+                                  for k, v in sorted(by_kind.items(), key=lambda kv: -kv[1][1])[:20]}}
 
-    # ---- end to end through the public API with host buffers ------------------------------------------------
-    def e2e_step(x_host):
-        x = x_host.to(dev, non_blocking=True).to(torch.bfloat16)
-        logits = step(x)
-        return logits.argmax(dim=-1).cpu()          # device->host read of the step's result (greedy token ids)
 
-    for i in range(2):
-        e2e_step(host_inputs[i % n_in])
-    barrier()
-    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    s0.record()
-    for i in range(args.steps):
-        toks = e2e_step(host_inputs[i % n_in])
-    s1.record()
-    barrier()
-    te = torch.tensor([s0.elapsed_time(s1)], device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_ms = te.item() / args.steps
-    e2e = {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT,
-           "h2d_bytes_per_step": host_inputs[0].numel() * 4, "d2h_bytes_per_step": toks.numel() * 8,
-           "ms_per_step": e2e_ms, "api": "AdapterRouter.forward(input_features, decoder_input_ids)"}
+def run_routed_leg(D: Dist, wl: Workload, steps: int, warmup: int, with_e2e: bool, sampler_on: bool):
+    """Device-resident (and optionally end-to-end) timing of one routed-forward workload.  Returns a dict."""
+    import torch
+
+    from speech_adapter_routing_b200 import ops, whisper_blocks
+
+    dev, world = D.dev, D.world
+    router, cfg, clips, g = build_b200_workload(wl, dev, seed=1234 + D.rank)
+    B = wl.batch
+    n_in = 3   # rotate input buffers; every activation tensor (B*1500*d*2 B >= 147 MB) already exceeds the 126 MB L2
+    langs = [[(i + j) % wl.adapters for i in range(B)] for j in range(n_in)]
+    host_inputs = [clips(B, langs[j], g).pin_memory() for j in range(n_in)]          # fp32, as a data loader yields
+    dev_inputs = [h.to(dev).to(torch.bfloat16) for h in host_inputs]
+    dec = torch.randint(5, cfg.vocab_size, (B, T_DEC), generator=g)
+    dec[:, 0] = cfg.decoder_start_token_id
+    dec_dev = dec.to(dev)
+
+    def step(x):
+        with torch.no_grad():
+            return router(x, decoder_input_ids=dec_dev)["logits"]
+
+    for i in range(warmup):
+        step(dev_inputs[i % n_in])
+    D.barrier()
+    sampler = ClockSampler(D.local_rank) if (sampler_on and D.rank == 0) else None
+    ops.reset_counters()
+    ops.K1_TIMELINE = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.time()
+    torch.cuda.nvtx.range_push("timed")
+    e0.record()
+    for i in range(steps):
+        step(dev_inputs[i % n_in])
+    e1.record()
+    D.barrier()
+    torch.cuda.nvtx.range_pop()
+    t_wall1 = time.time()
+    clocks = sampler.stop(t_wall0, t_wall1) if sampler else None
+    timeline, ops.K1_TIMELINE = ops.K1_TIMELINE, None
+    launches = sum(ops.LAUNCHES.values())
+    ms_total = e0.elapsed_time(e1)
+    ms_step = D.max_ms(ms_total) / steps
+    peaks, peak_src = load_peaks()
+    d = cfg.d_model
+    roof = qkv_roofline(timeline, B * 1500, d, wl.rank, ms_total, peaks, peak_src)
+    fused_lnu = whisper_blocks.FUSED_LN_U and ops.layernorm_lora_u_supported(d, wl.rank, 2)
+    roof["kernel"] = ("sar_attn_proj_fwd q|k|v + routed LoRA (M=%d, %d->%d, r=%d): " % (B * 1500, d, 3 * d, wl.rank)) + (
+        "ONE launch, k1v2<256,AUG> dense tiles with the low-rank term as one extra K block; U = scale·x·A_kᵀ comes from the "
+        "fused LayerNorm kernel (its 2·M·r·d·2 flops are not credited here)" if fused_lnu else
+        "two launches, k1v2 U pass + k1v2<256,AUG> dense tiles")
+    out = {"value": world * B / (ms_step * 1e-3), "ms_per_step": ms_step, "clocks": clocks, "gpu_launches": launches,
+           "roofline": roof, "d_model": d}
+
+    if with_e2e:
+        def e2e_step(x_host):
+            x = x_host.to(dev, non_blocking=True).to(torch.bfloat16)
+            logits = step(x)
+            return logits.argmax(dim=-1).cpu()          # device->host read of the step's result (greedy token ids)
+
+        for i in range(2):
+            e2e_step(host_inputs[i % n_in])
+        D.barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for i in range(steps):
+            toks = e2e_step(host_inputs[i % n_in])
+        s1.record()
+        D.barrier()
+        e2e_ms = D.max_ms(s0.elapsed_time(s1)) / steps
+        out["e2e"] = {"value": world * B / (e2e_ms * 1e-3), "unit": UNIT,
+                      "h2d_bytes_per_step": host_inputs[0].numel() * 4, "d2h_bytes_per_step": toks.numel() * 8,
+                      "ms_per_step": e2e_ms, "api": "AdapterRouter.forward(input_features, decoder_input_ids)"}
+
+    # ---- HBM-bound kernels of the path, timed alone on tensors of the step's shapes (burst HBM peak)
+    hbm_peak = float(peaks.get("hbm_gbs", FALLBACK_PEAKS["hbm_gbs"]))
+
+    def time_alone(fn, iters=10):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(iters):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / iters
+
+    hs = [torch.randn(B, 1500, d, device=dev, dtype=torch.bfloat16) for _ in range(2)]
+    it = [0]
+
+    def nxt():
+        it[0] += 1
+        return hs[it[0] % 2]
+    clf = router.classifier
+    ms_k2 = time_alone(lambda: clf.route_batch(nxt()))
+    k2_bytes = 2.0 * B * 1500 * d
+    out["roofline_router"] = {"bound": "hbm", "kernel": "sar_router_fwd (k2_pool + k2_head): LayerNorm -> mean over T -> MLP -> softmax -> argmax -> segments",
+                              "achieved": k2_bytes / (ms_k2 * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                              "frac": k2_bytes / (ms_k2 * 1e-3) / 1e9 / hbm_peak, "us": ms_k2 * 1e3,
+                              "algorithmic_bytes": k2_bytes, "note": "both launches + output allocation, timed alone"}
+    if fused_lnu:
+        layer = router.whisper.model.encoder.layers[0]
+        qkv = layer._sar_pack["self"].qkv.get()
+        ln = layer._sar_pack["ln1"].get()
+        idx = torch.tensor(langs[0], dtype=torch.int32, device=dev)
+        ms_lnu = time_alone(lambda: ops.layernorm_lora_u_fwd(nxt(), ln.W, ln.b, qkv.A, idx, qkv.n_sets, qkv.scale))
+        ms_ln = time_alone(lambda: ops.layernorm_fwd(nxt(), ln.W, ln.b))
+        lnu_bytes = 4.0 * B * 1500 * d + 2.0 * B * 1500 * wl.rank * qkv.n_sets
+        out["roofline_ln_u"] = {"bound": "hbm", "kernel": "sar_layernorm_lora_u_fwd: LayerNorm + U = scale·x·A_kᵀ for q and v in one pass over h",
+                                "achieved": lnu_bytes / (ms_lnu * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                                "frac": lnu_bytes / (ms_lnu * 1e-3) / 1e9 / hbm_peak, "us": ms_lnu * 1e3,
+                                "algorithmic_bytes": lnu_bytes, "plain_layernorm_us": ms_ln * 1e3}
+    del router, dev_inputs, host_inputs, hs
+    gc.collect()
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_train_leg(D: Dist, steps: int, warmup: int):
+    """BASELINE configs[4]: whisper-small LoRA r16 training step — forward + LoRA-only backward (K1 / K3 through autograd,
+    bf16 base, fp32 adapters, gradient checkpointing as in WhisperLoRA's default), 16 clips per GPU, the flat fp32
+    adapter-gradient bucket all-reduced over NCCL (src/training/trainer.py:251-277 semantics: clip after the reduce)."""
+    import torch
+
+    os.environ.setdefault("SAR_RANDOM_INIT", "1")
+    import speech_adapter_routing_b200 as sar
+    from speech_adapter_routing_b200 import ops
+    from speech_adapter_routing_b200.dist import FlatGradBucket
+
+    dev, world = D.dev, D.world
+    w = sar.WhisperLoRA("whisper-small", lora_r=16, lora_alpha=32, lora_dropout=0.0, device=str(dev),
+                        use_gradient_checkpointing=True)
+    w.train()
+    cfg = w.model.config
+    params = [p for p in w.model.parameters() if p.requires_grad]
+    bucket = FlatGradBucket(params)
+    opt = torch.optim.AdamW(params, lr=1e-4)
+    g = torch.Generator().manual_seed(100 + D.rank)
+    B = 16
+    xs = [torch.randn(B, cfg.num_mel_bins, 3000, generator=g).to(dev).to(torch.bfloat16) for _ in range(2)]
+    labels = torch.randint(5, cfg.vocab_size, (B, T_DEC), generator=g).to(dev)
+    ar = []
+
+    def step(i, timed=False):
+        bucket.zero_()
+        loss = w(input_features=xs[i % 2], labels=labels).loss
+        loss.backward()
+        if timed and world > 1:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            bucket.all_reduce_mean()
+            b.record()
+            ar.append((a, b))
+        else:
+            bucket.all_reduce_mean()
+        bucket.clip_grad_norm_(1.0)
+        opt.step()
+        return loss
+
+    for i in range(warmup):
+        step(i)
+    D.barrier()
+    ops.reset_counters()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        loss = step(i, timed=True)
+    e1.record()
+    D.barrier()
+    ms = D.max_ms(e0.elapsed_time(e1)) / steps
+    out = {"metric": "whisper_small_lora_r16_train_step_clips_per_sec", "value": world * B / (ms * 1e-3), "unit": UNIT,
+           "ms_per_step": ms, "batch_per_gpu": B, "t_dec": T_DEC, "steps": steps, "gradient_checkpointing": True,
+           "loss": float(loss), "trainable_params": sum(p.numel() for p in params),
+           "allreduce_bytes": bucket.buffer.numel() * 4, "libsar_launches": {k: v for k, v in ops.LAUNCHES.items() if v},
+           "scaling": "weak"}
+    if ar:
+        ar_ms = statistics.mean(a.elapsed_time(b) for a, b in ar)
+        out["allreduce"] = {"backend": "nccl", "ms": ar_ms, "share_of_step": ar_ms / ms,
+                            "algbw_gbs": bucket.buffer.numel() * 4 / (ar_ms * 1e-3) / 1e9,
+                            "note": "one in-place all-reduce of the flat bucket + 1/world scale, after backward, before the clip"}
+    del w, opt, bucket, xs
+    gc.collect()
+    torch.cuda.empty_cache()
+    return out
+
+
+def run_b200_arm(args):
+    import torch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200: the product path has no CPU fallback")
+    from speech_adapter_routing_b200 import _lib
+
+    D = Dist()
+    if _lib.lib().sar_device_ok() != 1:
+        raise SystemExit("libsar: device is not sm_100")
+    wl = Workload(args.model, args.adapters, args.rank, args.batch)
+    head = run_routed_leg(D, wl, args.steps, args.warmup, with_e2e=True, sampler_on=True)
+    default_shape = (wl.model, wl.rank, wl.batch) == (HEADLINE.model, HEADLINE.rank, HEADLINE.batch)
+    head["roofline"]["traffic"] = K1_DRAM_TRAFFIC.get("bytes") if default_shape else None
+    head["roofline"]["traffic_source"] = K1_DRAM_TRAFFIC.get("source") if default_shape else None
+
+    extra = {}
+    if args.extras != "none" and default_shape:
+        legs = ["medium", "large_v3", "train", "gpu_eager_baseline"] if args.extras == "all" else args.extras.split(",")
+        for name in legs:
+            try:
+                t0 = time.time()
+                if name in EXTRA_WORKLOADS:
+                    ewl = EXTRA_WORKLOADS[name]
+                    r = run_routed_leg(D, ewl, args.extra_steps, 3, with_e2e=False, sampler_on=False)
+                    extra[name] = {"workload": ewl.name, "batch_per_gpu": ewl.batch, "steps": args.extra_steps,
+                                   "value": r["value"], "unit": UNIT, "ms_per_step": r["ms_per_step"], "scaling": "weak",
+                                   "gpu_launches": r["gpu_launches"], "roofline": {k: v for k, v in r["roofline"].items()
+                                                                                   if k != "all_tcgen05_gemms"},
+                                   "roofline_router": r["roofline_router"]}
+                elif name == "train":
+                    extra[name] = run_train_leg(D, args.extra_steps + 2, 3)
+                elif name == "gpu_eager_baseline" and D.world == 1:
+                    extra[name] = gpu_eager_baseline(D.dev)
+                if name in extra:
+                    extra[name]["leg_seconds"] = time.time() - t0
+            except Exception as exc:   # an extra leg never takes the headline down
+                extra[name] = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+                gc.collect()
+                torch.cuda.empty_cache()
 
     # ---- informational: the log-mel front-end (waveform -> input_features on the GPU, sar_logmel_fwd); the metric
     # itself is quoted from log-mel inputs like the reference's model API takes them
@@ -370,52 +598,50 @@ def run_b200_arm(args):
     try:
         from speech_adapter_routing_b200 import logmel
 
-        wav = 0.1 * torch.randn(B, logmel.N_SAMPLES, device=dev)
+        n_mels = 128 if "large" in wl.model else 80
+        wav = 0.1 * torch.randn(wl.batch, logmel.N_SAMPLES, device=D.dev)
         for _ in range(2):
-            logmel.log_mel_spectrogram(wav, n_mels=cfg.num_mel_bins)
+            logmel.log_mel_spectrogram(wav, n_mels=n_mels)
         torch.cuda.synchronize()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
         for _ in range(3):
-            logmel.log_mel_spectrogram(wav, n_mels=cfg.num_mel_bins)
+            logmel.log_mel_spectrogram(wav, n_mels=n_mels)
         f1.record()
         torch.cuda.synchronize()
         lm_ms = f0.elapsed_time(f1) / 3
-        frontend = {"logmel_ms_per_batch": lm_ms, "clips_per_s_from_waveform": world * B / ((ms_step + lm_ms) * 1e-3),
+        frontend = {"logmel_ms_per_batch": lm_ms,
+                    "clips_per_s_from_waveform": D.world * wl.batch / ((head["ms_per_step"] + lm_ms) * 1e-3),
                     "note": "sar_logmel_fwd on [B, 480000] fp32 waveforms resident in HBM, added to ms_per_step"}
         del wav
     except Exception as exc:   # never let the informational leg take the bench line down
         frontend = {"error": f"{type(exc).__name__}: {exc}"[:200]}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.skip_cpu_baseline:
+    if D.rank == 0 and D.world == 1 and not args.skip_cpu_baseline:
         cpu = cpu_baseline()
 
-    if rank == 0:
+    if D.rank == 0:
+        from speech_adapter_routing_b200 import whisper_blocks
+
+        own_enc_attn = whisper_blocks.OWN_ATTN_MAX_TQ >= 1500
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "metric": METRIC, "value": head["value"], "unit": UNIT, "n_gpus": D.world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": B, "global_batch": world * B, "t_dec": T_DEC,
-                       "parallelism": f"utterance-sharded x{world}, adapters replicated, no data-path collective",
-                       "l2": "inputs rotate over 3 buffers; each activation tensor (147 MB) exceeds the 126 MB L2",
+            "config": {"workload": wl.name, "batch_per_gpu": wl.batch, "global_batch": D.world * wl.batch, "t_dec": T_DEC,
+                       "parallelism": f"utterance-sharded x{D.world}, adapters replicated, no data-path collective",
+                       "l2": "inputs rotate over 3 buffers; each activation tensor (>= 147 MB) exceeds the 126 MB L2",
                        "weights": "random-init",
-                       "rest_of_model": "libsar kernels for every projection / FFN / LayerNorm / conv front-end / lm head and the decoder's attention; encoder 1500x1500 softmax(QK^T)V = torch SDPA (cuDNN); embedding gathers = torch"},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
-            "frontend": frontend,
+                       "rest_of_model": "libsar kernels for every projection / FFN / LayerNorm / conv front-end / lm head and the decoder's attention; encoder 1500x1500 softmax(QK^T)V = "
+                                        + ("libsar fa_fwd_kernel" if own_enc_attn else "torch SDPA (cuDNN)") + "; embedding gathers = torch"},
+            "clocks": head["clocks"], "e2e": head["e2e"], "gpu_launches": head["gpu_launches"],
+            "roofline": head["roofline"], "roofline_router": head.get("roofline_router"),
+            "roofline_ln_u": head.get("roofline_ln_u"), "cpu_baseline": cpu, "frontend": frontend, "extra": extra,
         }
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
-
-
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE call of the roofline op (fused q|k|v + routed LoRA, M = 96000,
-# 768 -> 2304, r = 16, split path = two launches), from the `ncu --set full` capture summarised in
-# profiles/r01_v5_pair_kernel_ncu_full_summary.csv: U pass 147.7 MB read + 5.9 MB written, dense AUG kernel 178.2 MB
-# read + 390.5 MB written.  Algorithmic bytes = x 147.5 + y 442.4 + W 3.5 + adapters 0.3 = 593.7 MB; the surplus is
-# the second read of x by the U pass (the single-launch kernel that keeps U on chip moves 584 MB but runs at 52 %
-# tensor-active instead of 74 %: DESIGN.md §4).
-K1_DRAM_TRAFFIC_BYTES = 722.3e6
+    if D.world > 1:
+        D.dist.destroy_process_group()
 
 
 def main():
@@ -426,13 +652,13 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--ref-batch", type=int, default=2, help="clips per step of the reference (CPU) arm")
-    ap.add_argument("--model", default=MODEL, help="profiling only: whisper-medium / whisper-large-v3 (default: config 2)")
-    ap.add_argument("--adapters", type=int, default=N_ADAPTERS)
-    ap.add_argument("--rank", type=int, default=RANK_R)
-    ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="clips per GPU")
+    ap.add_argument("--extras", default="all", help="all | none | comma list of medium,large_v3,train,gpu_eager_baseline")
+    ap.add_argument("--extra-steps", type=int, default=3, help="timed steps of each extra leg")
+    ap.add_argument("--model", default=HEADLINE.model, help="profiling only: whisper-medium / whisper-large-v3 (default: config 2)")
+    ap.add_argument("--adapters", type=int, default=HEADLINE.adapters)
+    ap.add_argument("--rank", type=int, default=HEADLINE.rank)
+    ap.add_argument("--batch", type=int, default=HEADLINE.batch, help="clips per GPU")
     args = ap.parse_args()
-    if (args.model, args.adapters, args.rank, args.batch) != (MODEL, N_ADAPTERS, RANK_R, BATCH_PER_GPU):
-        configure(args.model, args.adapters, args.rank, args.batch)
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     # the CPU arm is ~seconds per clip: bound its run to a few minutes whatever K/W the caller passes
     args.steps_ref = min(args.steps, 5)

@@ -43,6 +43,9 @@ typedef enum sar_status {
 /* flags for sar_qv_lora_fwd* */
 #define SAR_FLAG_NONE 0u
 #define SAR_FLAG_SAVE_U 1u /* also write u = scale*(x·A_k^T) (bf16 [B*T, r]) to ws for the backward */
+/* sar_attn_proj_fwd, split path (ws != NULL): */
+#define SAR_FLAG_U_READY 4u /* ws already holds U (e.g. written by sar_layernorm_lora_u_fwd): run the dense launch only */
+#define SAR_FLAG_U_ONLY 8u  /* run only the U pass (U = scale·x·A_kᵀ of every set into ws); y is not written */
 
 /* ops for sar_workspace_bytes */
 typedef enum sar_op {
@@ -108,7 +111,7 @@ int sar_qv_lora_fwd(const void* x, const void* W, const void* bias, const void* 
  *   ws   NULL: single launch, the rank-r intermediate U never leaves the SM (TMEM -> shared memory -> MMA operand);
  *        the TMEM budget (two accumulator buffers + U) then limits the tile to 128/192 columns.
  *        non-NULL (sar_workspace_bytes(SAR_OP_ATTN_PROJ_FWD, B*T, T, d_in, r, n_sets) bytes): split path — launch 1
- *        writes U = scale·x·A_kᵀ of every set to ws (bf16 [B,T,64*n_sets]), launch 2 is the dense 256-wide kernel with
+ *        writes U = scale·x·A_kᵀ of every set to ws (bf16 [n_sets][B,T,r]), launch 2 is the dense 256-wide kernel with
  *        the low-rank term as one extra K block per tile.  Same rounding points, bit-identical results; measured
  *        ~1.9x faster at whisper-large-v3 shapes.
  */
@@ -242,6 +245,21 @@ int sar_dense_fwd(const void* x, int64_t ldx, int64_t x_batch_stride, const void
  */
 int sar_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, int64_t M, int d, float eps,
                       void* stream);
+
+/*
+ * LayerNorm fused with the LoRA down-projection of the attention projections that consume it (one pass over h):
+ *   x[b,t,:]    = LayerNorm(h[b,t,:])                                   bf16 [B, T, d]   (as sar_layernorm_fwd)
+ *   u[s][b,t,:] = bf16(scale · x[b,t,:] · A_cat[s*n_adapters + k]ᵀ)     bf16 [n_sets][B, T, r],  k = utt_adapter[b]
+ * u is exactly the workspace layout of sar_attn_proj_fwd's split path: pass it as `ws` with SAR_FLAG_U_READY and the
+ * U pass (a second read of all of x) disappears.  Replaces nn.LayerNorm ($HF/modeling_whisper.py:392, :470, :483) +
+ * PEFT's lora_A(x) at q_proj / v_proj (src/models/whisper_lora.py:88-98) for the layers' pre-attention norms.
+ * Utterances with k < 0 or k >= n_adapters get x only (their u rows are not written and never read).
+ * Constraints: d / 32 in {8, 12, 16, 24}; n_sets * r / 16 in {1, 2}; sar_layernorm_lora_u_supported() tells.
+ */
+int sar_layernorm_lora_u_fwd(const void* h, const void* gamma, const void* beta, void* x, const void* A_cat,
+                             const int32_t* utt_adapter, void* u, int B, int T, int d, int r, int n_sets,
+                             int n_adapters, float scale, float eps, void* stream);
+int sar_layernorm_lora_u_supported(int d, int r, int n_sets);
 
 /*
  * Row-indexed variant for decode steps (T = 1 per utterance, rows of different adapters share a tile):

@@ -17,6 +17,7 @@ LIB_PATH = CSRC_DIR / "libsar.so"
 
 SAR_OK, SAR_EINVAL, SAR_EARCH, SAR_ECUDA, SAR_EWORKSPACE = 0, -1, -2, -3, -4
 SAR_FLAG_SAVE_U = 1
+SAR_FLAG_U_READY, SAR_FLAG_U_ONLY = 4, 8
 SAR_OP_QV_LORA_FWD, SAR_OP_ROUTER_FWD, SAR_OP_QV_LORA_BWD, SAR_OP_QV_LORA_FWD_ROWS, SAR_OP_ATTN_PROJ_FWD = 0, 1, 2, 3, 4
 SAR_RPAD = 64
 SAR_ACT_NONE, SAR_ACT_GELU = 0, 1
@@ -39,6 +40,8 @@ _SIGNATURES = {
     "sar_decode_cross_attn": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_void_p]),
     "sar_logmel_fwd": (c_int, [c_void_p] * 8 + [c_int] * 4 + [c_void_p]),
     "sar_layernorm_fwd": (c_int, [c_void_p] * 4 + [c_int64, c_int, c_float, c_void_p]),
+    "sar_layernorm_lora_u_fwd": (c_int, [c_void_p] * 7 + [c_int] * 6 + [c_float, c_float, c_void_p]),
+    "sar_layernorm_lora_u_supported": (c_int, [c_int] * 3),
     "sar_qv_lora_fwd_rows": (c_int, [c_void_p] * 5 + [c_void_p, c_void_p] + [c_int] * 5 + [c_float, c_void_p, c_void_p]),
     "sar_router_fwd": (c_int, [c_void_p, c_int] + [c_void_p] * 12 + [c_int] * 6 + [c_void_p] * 5 + [c_void_p, c_void_p]),
     "sar_qv_lora_bwd": (c_int, [c_void_p] * 7 + [c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 6 + [c_float, c_void_p, c_void_p]),

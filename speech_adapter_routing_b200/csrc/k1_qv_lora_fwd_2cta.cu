@@ -57,7 +57,7 @@ struct K1V2Params {
   int act;                         // SAR_ACT_*: 0 none, 1 erf-GELU applied to (acc + bias) before the residual
   __nv_bfloat16* u_out;
   int u_only;        // LORA kernels: compute and save U = scale·X·A_kᵀ only (no output tiles): the split path's first launch
-  int u_ld;          // > 0: u_out is [B, T, u_ld] with set s at columns [64 s, 64 s + r); 0: legacy [B*T, r], set 0 only
+  int u_ld;          // > 0: u_out is [n_sets][B, T, u_ld = r] (one compact plane per LoRA set); 0: legacy [B*T, r], set 0 only
 };
 
 enum : int { EPI_RES = 1, EPI_GELU = 2, EPI_SCALE = 4 };
@@ -247,7 +247,9 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
               uint8_t* st = stages + stage * stage_bytes;
               const uint32_t full_leader = leader_addr(&full[stage]);
               if (leader) mbar_arrive_expect_tx(&full[stage], 2 * (V2_X_BYTES + L::WH_BYTES));
-              tma_load_3d_2sm(st, &tm_a, full_leader, set * 64, m0, b);
+              // U plane of this set: rows of r elements; the box is 64 wide, columns >= r are out of bounds -> zero-filled
+              // in shared memory WITHOUT being fetched (the extra K block costs r/64 of a regular stage's L2 traffic)
+              tma_load_3d_2sm(st, &tm_a, full_leader, 0, m0, set * p.B + b);
               tma_load_2d_2sm(st + V2_X_BYTES, &tm_b, full_leader, 0,
                               (set * p.n_adapters + k) * p.d_out + (nt_first % NTS) * BLOCK_N + half * (BLOCK_N / 2));
               if (++stage == S) {
@@ -421,8 +423,8 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
               st_shared_v4(u_row + (((2 * j) ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
               st_shared_v4(u_row + (((2 * j + 1) ^ sw) << 4), pk[4], pk[5], pk[6], pk[7]);
             }
-            if (save && (s == 0 || p.u_ld > 0)) {   // u_ld layout: set s occupies columns [64 s, 64 s + r)
-              uint4* ud = u_dst + (p.u_ld > 0 ? 8 * s : 0);
+            if (save && (s == 0 || p.u_ld > 0)) {   // u_ld layout: set s is plane s of [n_sets][B, T, r]
+              uint4* ud = u_dst + static_cast<size_t>(s) * p.B * p.T * (u_row_ld >> 3);
               ud[2 * j] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
               ud[2 * j + 1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
             }
@@ -604,7 +606,7 @@ static int k1v2_launch(const K1Args& a, cudaStream_t stream) {
   const uint64_t y_bs = a.y_batch_stride > 0 ? a.y_batch_stride : static_cast<uint64_t>(a.T) * ldy;
   p.act = a.act;
   p.u_out = (LORA && (n_sets == 1 || a.u_ld > 0)) ? reinterpret_cast<__nv_bfloat16*>(a.u_out) : nullptr;
-  if (p.u_only && (!p.u_out || a.u_ld < n_sets * 64)) return fail(SAR_EINVAL, "k1v2: U-only pass needs u_out [B,T,>=64*n_sets]");
+  if (p.u_only && (!p.u_out || a.u_ld != p.r)) return fail(SAR_EINVAL, "k1v2: U-only pass needs u_out [n_sets][B,T,r]");
 
   const int stage_bytes = L::stage_bytes(p.r, n_sets);
   const int budget = dev.max_smem_optin - 1024 - L::fixed_bytes(n_sets);
@@ -659,12 +661,12 @@ static int k1v2_launch(const K1Args& a, cudaStream_t stream) {
     if ((rc = make_tmap_bf16(&tm_w, a.W, 2, dims, strides, box))) return rc;
   }
   if (has_lora) {
-    if constexpr (AUG) {   // tm_a = the precomputed U, [B, T, u_ld]: one 64-column block per LoRA set
-      if (!a.u_out || a.u_ld < n_sets * 64 || a.u_ld % 8) return fail(SAR_EINVAL, "k1v2: AUG needs u [B,T,u_ld>=64*n_sets]");
-      const uint64_t dims[3] = {(uint64_t)n_sets * 64, (uint64_t)a.T, (uint64_t)a.B};
-      const uint64_t strides[2] = {(uint64_t)a.u_ld * 2, (uint64_t)a.T * a.u_ld * 2};
+    if constexpr (AUG) {   // tm_a = the precomputed U, [n_sets][B, T, r]: inner extent r < the 64-wide box
+      if (!a.u_out || a.u_ld != a.r) return fail(SAR_EINVAL, "k1v2: AUG needs u [n_sets][B,T,r]");
+      const uint64_t dims[3] = {(uint64_t)a.r, (uint64_t)a.T, (uint64_t)n_sets * a.B};
+      const uint64_t strides[2] = {(uint64_t)a.r * 2, (uint64_t)a.T * a.r * 2};
       const uint32_t box[3] = {64, V2_ROWS_PER_CTA, 1};
-      if ((rc = make_tmap_bf16(&tm_a, a.u_out, 3, dims, strides, box))) return rc;
+      if ((rc = make_tmap_bf16(&tm_a, a.u_out, 3, dims, strides, box, /*l2_promotion_bytes=*/0))) return rc;
     } else {
       const uint64_t dims[2] = {(uint64_t)a.d_in, (uint64_t)n_sets * a.n_adapters * a.r};
       const uint64_t strides[1] = {(uint64_t)a.d_in * 2};
@@ -672,10 +674,12 @@ static int k1v2_launch(const K1Args& a, cudaStream_t stream) {
       if ((rc = make_tmap_bf16(&tm_a, a.A_stack, 2, dims, strides, box))) return rc;
     }
     {
-      const uint64_t dims[2] = {(uint64_t)SAR_RPAD, (uint64_t)n_sets * a.n_adapters * a.d_out};
+      // lora_B is stored rank-padded to 64 (one swizzle layout for every rank); the map's inner extent is the true
+      // rank, so the padding columns are zero-filled on chip instead of being read
+      const uint64_t dims[2] = {(uint64_t)a.r, (uint64_t)n_sets * a.n_adapters * a.d_out};
       const uint64_t strides[1] = {(uint64_t)SAR_RPAD * 2};
       const uint32_t box[2] = {64, BLOCK_N / 2};
-      if ((rc = make_tmap_bf16(&tm_b, a.Bp_stack, 2, dims, strides, box))) return rc;
+      if ((rc = make_tmap_bf16(&tm_b, a.Bp_stack, 2, dims, strides, box, /*l2_promotion_bytes=*/AUG ? 0 : 256))) return rc;
     }
   }
 
@@ -730,18 +734,22 @@ int k1v2_qv_lora_fwd(const K1Args& a, int block_n, cudaStream_t stream) {
     return fail(SAR_EINVAL, "k1v2: residual needs one row-major output segment");
   if (lora && a.u_ws != nullptr && !a.u_only) {
     // Split path (chosen by the caller passing a workspace): launch 1 = U-only pass of the LoRA kernel, U for every set
-    // to HBM ([B,T,64*n_sets] bf16: 2-3 % of the call's traffic); launch 2 = the DENSE kernel with the low-rank term as
+    // to HBM ([n_sets][B,T,r] bf16: r/d_in of x's bytes per set); launch 2 = the DENSE kernel with the low-rank term as
     // one extra K block per tile (AUG).  Measured against the single-launch kernel that keeps U in shared memory
     // (which is limited to 128/192-wide tiles by the TMEM budget and stalls once per unit on the U hand-over):
     // whisper-large-v3 q|k|v r64: 1460 us -> see DESIGN.md §4.
     if (a.residual || a.act != SAR_ACT_NONE) return fail(SAR_EINVAL, "k1v2: split LoRA path has no residual / activation");
     const int n_sets = a.n_sets > 0 ? a.n_sets : 1;
-    K1Args u = a;
-    u.u_only = 1; u.u_out = a.u_ws; u.u_ld = 64 * n_sets; u.x_head_major = a.x_head_major;
-    int rc = k1v2_launch<128, true, 0, 4>(u, stream);
-    if (rc) return rc;
+    if (a.u_phase != 2) {
+      K1Args u = a;
+      u.u_only = 1; u.u_out = a.u_ws; u.u_ld = a.r; u.x_head_major = a.x_head_major;
+      if (a.u_phase == 1)   // U only: the output maps are built but never used; point them at the workspace
+        for (int s = 0; s < 3; ++s) u.y_seg[s] = a.u_ws;
+      int rc = k1v2_launch<128, true, 0, 4>(u, stream);
+      if (rc || a.u_phase == 1) return rc;
+    }
     K1Args m = a;
-    m.u_out = a.u_ws; m.u_ld = 64 * n_sets;
+    m.u_out = a.u_ws; m.u_ld = a.r;
     int bn = a.block_n_override;
     if (bn != 128 && bn != 192 && bn != 256) bn = (a.d_out % 256 == 0) ? 256 : ((a.d_out % 192 == 0) ? 192 : 128);
     if (a.d_out % bn) return fail(SAR_EINVAL, "k1v2: d_out not divisible by BLOCK_N");

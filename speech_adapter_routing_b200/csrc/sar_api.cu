@@ -58,7 +58,7 @@ static EncodeTiledFn g_encode = nullptr;
 static std::once_flag g_encode_once;
 
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box) {
+                   const uint32_t* box, int l2_promotion_bytes) {
   std::call_once(g_encode_once, [] {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult qres;
@@ -78,7 +78,10 @@ int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t*
   }
   CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank), const_cast<void*>(base),
                         gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                        l2_promotion_bytes >= 256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B
+                                                  : (l2_promotion_bytes >= 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                                                               : CU_TENSOR_MAP_L2_PROMOTION_NONE),
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     snprintf(g_err, sizeof(g_err), "cuTensorMapEncodeTiled failed (CUresult %d, rank %d, dims %llu x %llu)", (int)r, rank,
              (unsigned long long)dims[0], (unsigned long long)dims[1]);
@@ -108,7 +111,7 @@ int64_t sar_workspace_bytes(int op, int64_t rows, int64_t T, int64_t d, int64_t 
     case SAR_OP_ROUTER_FWD: return k2_workspace_bytes(rows, T, d);
     case SAR_OP_QV_LORA_FWD_ROWS: return rows_workspace_bytes(rows, d, r);
     case SAR_OP_QV_LORA_BWD: return k3_workspace_bytes(rows, T, d, r, n);
-    case SAR_OP_ATTN_PROJ_FWD: return rows * 64 * (n > 0 ? n : 1) * 2;
+    case SAR_OP_ATTN_PROJ_FWD: return rows * (r > 0 ? r : 64) * (n > 0 ? n : 1) * 2;   // U: bf16 [n_sets][rows, r]
     default: fail(SAR_EINVAL, "sar_workspace_bytes: unknown op"); return SAR_EINVAL;
   }
 }
@@ -145,6 +148,8 @@ int sar_attn_proj_fwd(const void* x, int x_head_major, const void* W_cat, const 
   a.grid_override = static_cast<int>((flags >> 18) & 0x3FF);
   a.n_seg = n_seg; a.n_sets = n_sets; a.x_head_major = x_head_major; a.y_head_major = y_head_major;
   a.u_ws = ws;
+  a.u_phase = (flags & SAR_FLAG_U_ONLY) ? 1 : ((flags & SAR_FLAG_U_READY) ? 2 : 0);
+  if (a.u_phase && !ws) return fail(SAR_EINVAL, "sar_attn_proj_fwd: U_ONLY / U_READY need the U workspace");
   for (int s = 0; s < n_seg; ++s) {
     a.seg_set[s] = seg_set[s];
     a.seg_scale[s] = seg_scale[s];
@@ -269,6 +274,17 @@ int sar_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* 
   if (rc) return rc;
   return layernorm_fwd(x, gamma, beta, y, M, d, eps, static_cast<cudaStream_t>(stream));
 }
+
+int sar_layernorm_lora_u_fwd(const void* h, const void* gamma, const void* beta, void* x, const void* A_cat,
+                             const int32_t* utt_adapter, void* u, int B, int T, int d, int r, int n_sets,
+                             int n_adapters, float scale, float eps, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  return ln_lora_u_fwd(h, gamma, beta, x, A_cat, utt_adapter, u, B, T, d, r, n_sets, n_adapters, scale, eps,
+                       static_cast<cudaStream_t>(stream));
+}
+
+int sar_layernorm_lora_u_supported(int d, int r, int n_sets) { return ln_lora_u_supported(d, r, n_sets) ? 1 : 0; }
 
 int sar_qv_lora_fwd_rows(const void* x, const void* W, const void* bias, const void* A_stack, const void* Bp_stack,
                          const int32_t* row_adapter, void* y, int M, int d_in, int d_out, int r, int n_adapters,

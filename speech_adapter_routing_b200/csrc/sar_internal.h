@@ -30,8 +30,9 @@ int require_sm100();
 // Encode a bf16 tiled tensor map with 128-byte swizzle.  dims/box are innermost-first; strides (bytes) has rank-1
 // entries for dims 1..rank-1.  Uses cuTensorMapEncodeTiled resolved through cudaGetDriverEntryPoint, so libsar has
 // no link-time dependency on libcuda.
+// l2_promotion_bytes: 256 (default, streaming operands), 128, or 0 = none (narrow boxes whose rows are 32-128 bytes).
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                   const uint32_t* box);
+                   const uint32_t* box, int l2_promotion_bytes = 256);
 
 struct K1Args {
   const void* x;
@@ -64,9 +65,10 @@ struct K1Args {
   long long ldr, res_batch_stride;   // residual row stride (0 = d_out) / batch stride (0 = T*ldr)
   int res_broadcast;                 // 1: the same [T, d_out] residual for every b (positional embedding)
   // ---- split LoRA path: U to a caller workspace, then the dense kernel with one extra K block per tile
-  void* u_ws;        // bf16 [B, T, 64*n_sets] workspace, or null = single-launch kernel (U stays in shared memory)
+  void* u_ws;        // bf16 [n_sets][B, T, r] workspace, or null = single-launch kernel (U stays in shared memory)
+  int u_phase;       // split path: 0 = both launches, 1 = U pass only (y may be null), 2 = dense launch only (ws holds U)
   int u_only;        // internal: run only the U pass
-  int u_ld;          // internal: row stride of u_out in the [B, T, u_ld] layout
+  int u_ld;          // internal: > 0 = u_out is [n_sets][B, T, u_ld] with u_ld == r (one plane per LoRA set)
 };
 int k1_qv_lora_fwd(const K1Args& a, cudaStream_t stream);
 int k1v2_qv_lora_fwd(const K1Args& a, int block_n, cudaStream_t stream);
@@ -85,6 +87,10 @@ int logmel_fwd(const float* wave, const float* window, const float* cos_t, const
                cudaStream_t stream);
 int layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, int64_t M, int d, float eps,
                   cudaStream_t stream);
+int ln_lora_u_fwd(const void* h, const void* gamma, const void* beta, void* x, const void* A_cat,
+                  const int32_t* utt_adapter, void* u_out, int B, int T, int d, int r, int n_sets, int n_adapters,
+                  float scale, float eps, cudaStream_t stream);
+bool ln_lora_u_supported(int d, int r, int n_sets);
 
 struct K2Args {
   const void* h;

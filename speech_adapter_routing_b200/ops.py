@@ -124,7 +124,7 @@ def attn_proj_fwd(x: torch.Tensor, W_cat: torch.Tensor, bias_cat: Optional[torch
                   A_cat: Optional[torch.Tensor], Bp_cat: Optional[torch.Tensor], utt_adapter: Optional[torch.Tensor],
                   seg_set: Sequence[int], seg_scale: Sequence[float], n_sets: int, scale: float,
                   x_head_major: bool = False, y_head_major: bool = True, block_n: int = 0,
-                  grid: int = 0, split: Optional[bool] = None) -> List[torch.Tensor]:
+                  grid: int = 0, split: Optional[bool] = None, u: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
     """Fused attention projections (sar_attn_proj_fwd): up to three projections of the same x in one launch.
 
     x [B,T,d_in] (or [B,d_in/64,T,64] if ``x_head_major``); W_cat [n_seg*d_out, d_in]; A_cat [n_sets*n, r, d_in];
@@ -132,6 +132,7 @@ def attn_proj_fwd(x: torch.Tensor, W_cat: torch.Tensor, bias_cat: Optional[torch
     ``split=True``: U = scale·x·A_kᵀ goes through a [B,T,64*n_sets] workspace and the projections run on the dense
     256-wide kernel with one extra K block; ``split=False``: the single-launch kernel that keeps U in shared memory;
     ``None`` (default): split from SPLIT_MIN_ROWS rows up (bit-identical results either way).
+    ``u``: U already computed for this x ([n_sets, B, T, r], e.g. by ``layernorm_lora_u_fwd``): only the dense launch runs.
     """
     _need_cuda(x, W_cat, bias_cat, A_cat, Bp_cat, utt_adapter)
     x = _bf16c(x, "x"); W_cat = _bf16c(W_cat, "W_cat"); bias_cat = _bf16c(bias_cat, "bias_cat")
@@ -167,8 +168,13 @@ def attn_proj_fwd(x: torch.Tensor, W_cat: torch.Tensor, bias_cat: Optional[torch
     flags = ((block_n & 0x3FF) << 8) | ((grid & 0x3FF) << 18)
     has_lora = n_adapters > 0
     ws = None
-    if has_lora and (split if split is not None else B * T >= SPLIT_MIN_ROWS):
-        ws = torch.empty(B * T * 64 * n_sets, dtype=torch.bfloat16, device=x.device)
+    if has_lora and u is not None:
+        if u.dtype != torch.bfloat16 or not u.is_contiguous() or u.numel() != n_sets * B * T * r:
+            raise ValueError("u must be contiguous bf16 [n_sets, B, T, r]")
+        ws = u
+        flags |= _lib.SAR_FLAG_U_READY
+    elif has_lora and (split if split is not None else B * T >= SPLIT_MIN_ROWS):
+        ws = torch.empty(n_sets * B * T * r, dtype=torch.bfloat16, device=x.device)   # U: [n_sets][B, T, r]
 
     def launch():
         check(lib().sar_attn_proj_fwd(_ptr(x), int(x_head_major), _ptr(W_cat), _ptr(bias_cat),
@@ -177,10 +183,33 @@ def attn_proj_fwd(x: torch.Tensor, W_cat: torch.Tensor, bias_cat: Optional[torch
                                       n_sets if has_lora else 1, int(y_head_major), B, T, d_in, d_out, r, n_adapters,
                                       float(scale), flags, _ptr(ws), _stream(x)))
     n_lora = sum(1 for s in seg_set if s >= 0) if has_lora else 0
-    flops = 2.0 * B * T * d_in * d_out * n_seg + 2.0 * B * T * r * (n_sets * d_in + n_lora * d_out) * (n_lora > 0)
+    # algorithmic flops of THIS call: with U precomputed (fused into the LayerNorm kernel) the down-projection
+    # 2·M·r·d_in per set is not done here and is not credited to this kernel
+    flops = 2.0 * B * T * d_in * d_out * n_seg + 2.0 * B * T * r * ((0 if u is not None else n_sets * d_in) +
+                                                                     n_lora * d_out) * (n_lora > 0)
     _time_k1(K1_TIMELINE, "proj", B * T, d_in, n_seg * d_out, flops, launch)
-    LAUNCHES["proj"] += 2 if ws is not None else 1
+    LAUNCHES["proj"] += 2 if (ws is not None and u is None) else 1
     return ys
+
+
+def lora_u_fwd(x: torch.Tensor, A_cat: torch.Tensor, utt_adapter: torch.Tensor, n_sets: int, scale: float,
+               d_out: int) -> torch.Tensor:
+    """The U pass of the split path alone (SAR_FLAG_U_ONLY): U = scale·x·A_kᵀ, bf16 [n_sets, B, T, r], on the tcgen05
+    pair kernel.  ``d_out`` only sizes tensor maps that the pass never touches."""
+    _need_cuda(x, A_cat, utt_adapter)
+    x = _bf16c(x, "x"); A_cat = _bf16c(A_cat, "A_cat")
+    B, T, d_in = x.shape
+    n_adapters, r = A_cat.shape[0] // n_sets, A_cat.shape[1]
+    u = torch.empty(n_sets, B, T, r, dtype=torch.bfloat16, device=x.device)
+    yp = (ctypes.c_void_p * 1)(u.data_ptr())
+    ss = (ctypes.c_int32 * 1)(0)
+    sc = (ctypes.c_float * 1)(1.0)
+    dummy = torch.empty(16, dtype=torch.bfloat16, device=x.device)
+    check(lib().sar_attn_proj_fwd(_ptr(x), 0, _ptr(dummy), None, _ptr(A_cat), _ptr(dummy), _ptr(utt_adapter.contiguous()),
+                                  yp, ss, sc, 1, n_sets, 0, B, T, d_in, d_out, r, n_adapters, float(scale),
+                                  _lib.SAR_FLAG_U_ONLY, _ptr(u), _stream(x)))
+    LAUNCHES["proj"] += 1
+    return u
 
 
 def attn_proj_fwd_rows(x: torch.Tensor, W_cat: torch.Tensor, bias_cat: Optional[torch.Tensor],
@@ -353,6 +382,34 @@ def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps:
     check(lib().sar_layernorm_fwd(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), M, d, float(eps), _stream(x)))
     LAUNCHES["ln"] += 1
     return y
+
+
+def layernorm_lora_u_supported(d: int, r: int, n_sets: int) -> bool:
+    return bool(lib().sar_layernorm_lora_u_supported(int(d), int(r), int(n_sets)))
+
+
+def layernorm_lora_u_fwd(h: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, A_cat: torch.Tensor,
+                         utt_adapter: torch.Tensor, n_sets: int, scale: float,
+                         eps: float = 1e-5) -> Tuple[torch.Tensor, torch.Tensor]:
+    """x = LayerNorm(h) and U = scale·x·A_kᵀ for every LoRA set in one pass over h (sar_layernorm_lora_u_fwd).
+    h [B,T,d] bf16; A_cat [n_sets*n_adapters, r, d] bf16; returns (x [B,T,d], U [n_sets,B,T,r])."""
+    _need_cuda(h, gamma, beta, A_cat, utt_adapter)
+    h = _bf16c(h, "h"); gamma = _bf16c(gamma, "gamma"); beta = _bf16c(beta, "beta"); A_cat = _bf16c(A_cat, "A_cat")
+    if h.dim() != 3:
+        raise ValueError("h must be [B, T, d]")
+    B, T, d = h.shape
+    if A_cat.shape[0] % n_sets or A_cat.shape[2] != d:
+        raise ValueError("A_cat must be [n_sets*n_adapters, r, d]")
+    n_adapters, r = A_cat.shape[0] // n_sets, A_cat.shape[1]
+    if utt_adapter.dtype != torch.int32 or utt_adapter.numel() != B:
+        raise ValueError("utt_adapter must be int32 [B]")
+    x = torch.empty_like(h)
+    u = torch.empty(n_sets, B, T, r, dtype=torch.bfloat16, device=h.device)
+    check(lib().sar_layernorm_lora_u_fwd(_ptr(h), _ptr(gamma), _ptr(beta), _ptr(x), _ptr(A_cat),
+                                         _ptr(utt_adapter.contiguous()), _ptr(u), B, T, d, r, n_sets, n_adapters,
+                                         float(scale), float(eps), _stream(h)))
+    LAUNCHES["ln"] += 1
+    return x, u
 
 
 def qv_lora_fwd_rows(x: torch.Tensor, W: torch.Tensor, bias: Optional[torch.Tensor], A_stack: Optional[torch.Tensor],

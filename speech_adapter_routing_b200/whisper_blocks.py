@@ -35,6 +35,11 @@ from .lora_linear import RoutedLoRALinear
 from .routing import operand_epoch
 
 FUSED_BLOCKS_ENABLED = True   # debug switch: False restores HF's layer bodies everywhere
+FUSED_LN_U = os.environ.get("SAR_FUSED_LN_U", "1") != "0"   # LayerNorm + LoRA down-projection in one pass (A/B switch)
+# Test hook: the fused bodies call the kernels directly, so forward hooks on q_proj / v_proj never fire.  Set to a dict
+# to record, per projection MODULE (key: id(module)), what that module's forward would have returned — row-major
+# [B, T, d_out], before the query scale — for every fused projection call (tests/test_routed_whisper_gpu.py).
+PROJ_CAPTURE: Optional[Dict[int, List[torch.Tensor]]] = None
 
 
 # ------------------------------------------------------------------------------------------------ operand packing
@@ -113,7 +118,17 @@ class _ProjPack:
     def resolve_index(self, B: int, device) -> Optional[torch.Tensor]:
         return self.lora_mods[0].resolve_index(B, device) if self.lora_mods else None
 
-    def __call__(self, x: torch.Tensor, idx: Optional[torch.Tensor]) -> List[torch.Tensor]:
+    def fused_ln_u_ok(self, B: int, T: int, d: int, idx: Optional[torch.Tensor]) -> bool:
+        """True when the LayerNorm feeding this call may also produce U = scale·x·A_kᵀ (ops.layernorm_lora_u_fwd): the
+        split LoRA path would be taken and the fused kernel covers this (d, r, n_sets)."""
+        if not FUSED_LN_U or idx is None or self.A is None or (T == 1 and B > 1) or B * T < ops.SPLIT_MIN_ROWS:
+            return False
+        key = (d, self.A.shape[1], self.n_sets)
+        if getattr(self, "_lnu_key", None) != key:
+            self._lnu_key, self._lnu_ok = key, ops.layernorm_lora_u_supported(*key)
+        return self._lnu_ok
+
+    def __call__(self, x: torch.Tensor, idx: Optional[torch.Tensor], u: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
         lora = idx is not None and self.A is not None
         B, T, d = x.shape
         if T == 1 and B > 1:
@@ -124,9 +139,14 @@ class _ProjPack:
                                         self.seg_set if lora else [-1] * len(self.seg_set), self.kernel_scale,
                                         self.n_sets if lora else 1, self.scale)
             return [y.view(B, -1, 1, 64) for y in ys]
-        return ops.attn_proj_fwd(x, self.W, self.bias, self.A if lora else None, self.Bp if lora else None,
-                                 idx if lora else None, self.seg_set if lora else [-1] * len(self.seg_set),
-                                 self.kernel_scale, self.n_sets if lora else 1, self.scale, y_head_major=True)
+        ys = ops.attn_proj_fwd(x, self.W, self.bias, self.A if lora else None, self.Bp if lora else None,
+                               idx if lora else None, self.seg_set if lora else [-1] * len(self.seg_set),
+                               self.kernel_scale, self.n_sets if lora else 1, self.scale, y_head_major=True,
+                               u=u if lora else None)
+        if PROJ_CAPTURE is not None:
+            for m, y, s in zip(self.mods, ys, self.seg_scale):
+                PROJ_CAPTURE.setdefault(id(m), []).append((y.transpose(1, 2).reshape(B, T, -1).float() / s).detach())
+        return ys
 
 
 class _DensePack:
@@ -194,6 +214,18 @@ def _ln(x: torch.Tensor, pack: _DensePack, eps: float) -> torch.Tensor:
     return ops.layernorm_fwd(x, p.W, p.b, eps)
 
 
+def _ln_proj(h: torch.Tensor, pack: _DensePack, eps: float, proj: _ProjPack, idx: Optional[torch.Tensor]) -> List[torch.Tensor]:
+    """proj(LayerNorm(h)).  When the projection carries routed LoRA on the split path, the LayerNorm kernel also emits
+    U = scale·x·A_kᵀ while the normalised row is in registers, so the projection's U pass — a second read of all of x —
+    disappears (csrc/ln_lora_u.cu)."""
+    B, T, d = h.shape
+    if proj.fused_ln_u_ok(B, T, d, idx):
+        p = pack.get()
+        x, u = ops.layernorm_lora_u_fwd(h, p.W, p.b, proj.A, idx, proj.n_sets, proj.scale, eps)
+        return proj(x, idx, u=u)
+    return proj(_ln(h, pack, eps), idx)
+
+
 def _dense(x: torch.Tensor, pack: _DensePack, residual: Optional[torch.Tensor] = None, act: int = SAR_ACT_NONE,
            head_major: bool = False, inplace: bool = False) -> torch.Tensor:
     """act(x·Wᵀ + b) + residual.  Row-major inputs are flattened to one [1, B·T, d] "utterance" (no LoRA term, so
@@ -242,8 +274,7 @@ def _encoder_layer_forward(self, hidden_states: torch.Tensor, attention_mask: Op
     h = hidden_states.contiguous()
     B = h.shape[0]
     idx = qkv.resolve_index(B, h.device)
-    x = _ln(h, pk["ln1"], self.self_attn_layer_norm.eps)
-    q, k, v = qkv(x, idx)
+    q, k, v = _ln_proj(h, pk["ln1"], self.self_attn_layer_norm.eps, qkv, idx)
     o = _sdpa(q, k, v)
     h = _dense(o, pk["self"].out, residual=h, head_major=True)
     x = _ln(h, pk["ln3"], self.final_layer_norm.eps)
@@ -272,13 +303,11 @@ def _decoder_layer_forward(self, hidden_states: torch.Tensor, attention_mask: Op
     h = hidden_states.contiguous()
     B = h.shape[0]
     idx = qkv.resolve_index(B, h.device)
-    x = _ln(h, pk["ln1"], self.self_attn_layer_norm.eps)
-    q, k, v = qkv(x, idx)
+    q, k, v = _ln_proj(h, pk["ln1"], self.self_attn_layer_norm.eps, qkv, idx)
     o = _sdpa(q, k, v, mask=attention_mask, causal=True)
     h = _dense(o, pk["self"].out, residual=h, head_major=True)
     if encoder_hidden_states is not None:
-        x = _ln(h, pk["ln2"], self.encoder_attn_layer_norm.eps)
-        (q,) = cq(x, cq.resolve_index(B, h.device))
+        (q,) = _ln_proj(h, pk["ln2"], self.encoder_attn_layer_norm.eps, cq, cq.resolve_index(B, h.device))
         k, v = ckv(encoder_hidden_states.contiguous(), ckv.resolve_index(B, h.device))
         o = _sdpa(q, k, v)
         h = _dense(o, pk["cross"].out, residual=h, head_major=True, inplace=True)

@@ -257,3 +257,86 @@ def test_logmel_matches_oracle(cuda_dev, n_mels, dtype, tol):
     # a clip processed alone gives identical values (the per-clip maximum never leaks across clips)
     one = logmel.log_mel_spectrogram([torch.from_numpy(clips[0]).to(cuda_dev)], n_mels=n_mels, dtype=dtype)
     assert torch.equal(one[0], out[0])
+
+
+# ------------------------------------------------------------------------------------------------ LayerNorm + LoRA-down (fused)
+LNU_CASES = [
+    # B, T, d, r, n_sets, n_adapters, base_only_every
+    (3, 1500, 768, 16, 2, 4, 0),      # whisper-small encoder q|k|v (BASELINE config 2 shape family)
+    (4, 128, 768, 16, 2, 4, 3),       # decoder self-attention rows, one base-only utterance
+    (5, 13, 768, 16, 1, 4, 0),        # cross-attention q: one set; ragged last 8-row group
+    (3, 100, 256, 16, 2, 3, 0),       # micro test geometry
+    (2, 37, 384, 16, 2, 2, 2),        # whisper-tiny
+    (2, 300, 512, 32, 1, 2, 0),       # whisper-base, r32, one set
+    (64, 128, 768, 16, 2, 4, 0),      # many short utterances: CTAs cross utterance boundaries, A_k re-staged
+]
+
+
+def test_layernorm_lora_u_support_matrix(libsar):
+    """d <= 768 with 16 or 32 rank columns over all sets; everything else keeps LayerNorm + the tcgen05 U pass."""
+    assert ops.layernorm_lora_u_supported(768, 16, 2) and ops.layernorm_lora_u_supported(384, 32, 1)
+    assert ops.layernorm_lora_u_supported(768, 16, 1) and ops.layernorm_lora_u_supported(256, 16, 2)
+    assert not ops.layernorm_lora_u_supported(1024, 32, 2) and not ops.layernorm_lora_u_supported(1280, 64, 2)
+    assert not ops.layernorm_lora_u_supported(768, 32, 2) and not ops.layernorm_lora_u_supported(768, 24, 1)
+
+
+@pytest.mark.parametrize("B,T,d,r,n_sets,n,bo", LNU_CASES)
+def test_layernorm_lora_u_fused_matches_layernorm_and_the_u_pass(cuda_dev, B, T, d, r, n_sets, n, bo):
+    """sar_layernorm_lora_u_fwd: x must be LayerNorm(h) (same arithmetic as sar_layernorm_fwd: at most a last-bit bf16
+    difference from the different fp32 summation order) and U = bf16(scale · x · A_kᵀ) for every LoRA set — the operand the
+    split path's dense kernel consumes (reference ops: nn.LayerNorm + PEFT lora_A at q_proj / v_proj)."""
+    assert ops.layernorm_lora_u_supported(d, r, n_sets)
+    g = torch.Generator().manual_seed(d + T)
+    h = (torch.randn(B, T, d, generator=g) * 1.5 + 0.3).to(torch.bfloat16)
+    gamma = (1.0 + 0.1 * torch.randn(d, generator=g)).to(torch.bfloat16)
+    beta = (0.1 * torch.randn(d, generator=g)).to(torch.bfloat16)
+    A = ((torch.rand(n_sets * n, r, d, generator=g) * 2 - 1) / d ** 0.5).to(torch.bfloat16)
+    idx = torch.randint(0, n, (B,), generator=g).to(torch.int32)
+    if bo:
+        idx[::bo] = -1
+    scale = 2.0
+    x, u = ops.layernorm_lora_u_fwd(h.to(cuda_dev), gamma.to(cuda_dev), beta.to(cuda_dev), A.to(cuda_dev),
+                                    idx.to(cuda_dev), n_sets, scale, 1e-5)
+    x, u = x.cpu(), u.cpu()
+    ref_ln = torch.nn.functional.layer_norm(h.float(), (d,), gamma.float(), beta.float(), 1e-5)
+    assert (x.float() - ref_ln).abs().max().item() <= 2.0 ** -5
+    x_plain = ops.layernorm_fwd(h.to(cuda_dev), gamma.to(cuda_dev), beta.to(cuda_dev), 1e-5).cpu()
+    diff = x.float() - x_plain.float()
+    assert diff.abs().max().item() <= 2.0 ** -7 * x_plain.float().abs().max().item()   # one bf16 ulp of the largest value
+    assert (diff != 0).float().mean().item() <= 2e-3
+    assert u.shape == (n_sets, B, T, r)
+    for s in range(n_sets):
+        for b in range(B):
+            k = int(idx[b])
+            if k < 0:
+                continue                                             # base-only utterance: U rows are never read
+            want = (scale * (x[b].float() @ A[s * n + k].float().t())).to(torch.bfloat16)
+            assert rel_err(u[s, b], want) <= TIGHT, (s, b)
+    # and against the tcgen05 U pass of the split path on the same x
+    if n_sets * B * T >= 1:
+        u_pass = ops.lora_u_fwd(x.to(cuda_dev), A.to(cuda_dev), idx.to(cuda_dev), n_sets, scale, d).cpu()
+        for b in range(B):
+            if int(idx[b]) >= 0:
+                assert rel_err(u[:, b], u_pass[:, b]) <= TIGHT
+
+
+def test_projection_with_precomputed_u_equals_the_two_launch_split_path(cuda_dev):
+    """sar_attn_proj_fwd with SAR_FLAG_U_READY (U from the fused LayerNorm) vs its own U pass: same dense launch, U equal
+    up to summation order -> outputs within one bf16 rounding."""
+    B, T, d, r, n = 4, 1500, 768, 16, 4
+    g = torch.Generator().manual_seed(5)
+    dev = cuda_dev
+    h = torch.randn(B, T, d, generator=g).to(torch.bfloat16).to(dev)
+    gamma = torch.ones(d, dtype=torch.bfloat16, device=dev)
+    beta = torch.zeros(d, dtype=torch.bfloat16, device=dev)
+    W = (torch.randn(3 * d, d, generator=g) * 0.02).to(torch.bfloat16).to(dev)
+    bias = (torch.randn(3 * d, generator=g) * 0.02).to(torch.bfloat16).to(dev)
+    A = ((torch.rand(2 * n, r, d, generator=g) * 2 - 1) / d ** 0.5).to(torch.bfloat16).to(dev)
+    Bp = ops.pack_lora_b((torch.randn(2 * n, d, r, generator=g) * 0.02).to(torch.bfloat16).to(dev))
+    idx = torch.tensor([0, 3, -1, 2], dtype=torch.int32, device=dev)
+    x, u = ops.layernorm_lora_u_fwd(h, gamma, beta, A, idx, 2, 2.0)
+    want = ops.attn_proj_fwd(x, W, bias, A, Bp, idx, [0, -1, 1], [1.0, 1.0, 1.0], 2, 2.0, split=True)
+    got = ops.attn_proj_fwd(x, W, bias, A, Bp, idx, [0, -1, 1], [1.0, 1.0, 1.0], 2, 2.0, u=u)
+    for a, b in zip(got, want):
+        assert rel_err(a, b) <= TIGHT
+    assert torch.equal(got[1], want[1])            # k_proj carries no adapter: bit-identical

@@ -12,6 +12,7 @@ top-1 / top-2 logit margin is below MARGIN_EPS (there the argmax of a bf16 path 
 later token depends on it); rows without such a position must be identical over their whole length.  No allowance
 for "most rows".
 """
+import contextlib
 import copy
 from pathlib import Path
 
@@ -31,6 +32,29 @@ MARGIN_EPS = 2e-2     # in units of max|logit| of the row's reference logits (bf
 def rel_err(y, ref):
     y, ref = y.float().cpu(), ref.float().cpu()
     return ((y - ref).abs().max() / ref.abs().max().clamp_min(1e-12)).item()
+
+
+@contextlib.contextmanager
+def capture_lora_modules(whisper):
+    """path -> [output of that q_proj / v_proj per call], whichever way the layer ran: forward hooks for HF's bodies
+    over the module slots, whisper_blocks.PROJ_CAPTURE for the fused bodies (which call the kernels directly)."""
+    from speech_adapter_routing_b200 import whisper_blocks as wb
+
+    mods = sar.lora_modules(whisper)
+    captured = {}
+    hooks = [m.register_forward_hook(lambda mod, inp, out, p=p: captured.setdefault(p, []).append(out.detach()))
+             for p, m in mods.items()]
+    wb.PROJ_CAPTURE = {}
+    try:
+        yield captured
+    finally:
+        by_id = {id(m): p for p, m in mods.items()}
+        for mid, outs in wb.PROJ_CAPTURE.items():
+            if mid in by_id:
+                captured.setdefault(by_id[mid], []).extend(outs)
+        wb.PROJ_CAPTURE = None
+        for hk in hooks:
+            hk.remove()
 
 
 class Setup:
@@ -76,18 +100,11 @@ def test_router_indices_bit_exact_and_logits_within_tolerance(micro, kind):
     x, dec, labels, langs = s.batch(8, 12, kind)
     ref = s.oracle.forward_hard(x, dec, labels, capture=True)
     xg = x.to(s.dev).to(torch.bfloat16)
-    captured = {}
-    hooks = [m.register_forward_hook(lambda mod, inp, out, p=p: captured.setdefault(p, []).append(out.detach()))
-             for p, m in sar.lora_modules(s.router.whisper).items()]
-    try:
-        with torch.no_grad():
-            h = s.router.extract_encoder_features(xg)
-            routed = s.router.detect_indices(h)
-            captured.clear()            # keep only the routed pass (the LID pass runs the same modules on base weights)
+    with torch.no_grad():
+        h = s.router.extract_encoder_features(xg)
+        routed = s.router.detect_indices(h)
+        with capture_lora_modules(s.router.whisper) as captured:   # routed pass only (the LID pass ran on base weights)
             out = s.router._hard_routing(xg, routed.idx, labels.to(s.dev))
-    finally:
-        for hk in hooks:
-            hk.remove()
     assert torch.equal(routed.idx.cpu().long(), ref["idx"])                       # bit-exact routing
     assert ref["idx"].tolist() == langs                                           # and it is the intended mix
     for p, want in ref["captured"].items():                                       # every LoRA'd module, both stacks
@@ -470,17 +487,10 @@ def _model_level_check(s, B, T_dec, kind, seed):
     x, dec, labels, langs = s.batch(B, T_dec, kind, seed=seed)
     ref = s.oracle.forward_hard(x, dec, labels, capture=True)
     xg = x.to(s.dev).to(torch.bfloat16)
-    captured = {}
-    hooks = [m.register_forward_hook(lambda mod, inp, out, p=p: captured.setdefault(p, []).append(out.detach()))
-             for p, m in sar.lora_modules(s.router.whisper).items()]
-    try:
-        with torch.no_grad():
-            routed = s.router.detect_indices(s.router.extract_encoder_features(xg))
-            captured.clear()
+    with torch.no_grad():
+        routed = s.router.detect_indices(s.router.extract_encoder_features(xg))
+        with capture_lora_modules(s.router.whisper) as captured:
             out = s.router._hard_routing(xg, routed.idx, labels.to(s.dev))
-    finally:
-        for hk in hooks:
-            hk.remove()
     assert torch.equal(routed.idx.cpu().long(), ref["idx"]) and ref["idx"].tolist() == langs
     assert rel_err(out["logits"], ref["logits"]) <= LOGIT_TOL
     assert abs(out["loss"].item() - ref["loss"].item()) <= 2e-2 * abs(ref["loss"].item())

@@ -568,6 +568,72 @@ def suite_perf2():
                 log(f"[perf2] d={d} SDPA {name}: unavailable ({type(e).__name__}: {str(e)[:80]})")
 
 
+def suite_lnu():
+    """Split LoRA path, piece by piece, at the bench shape: LayerNorm, LayerNorm+U (fused), the tcgen05 U pass, the dense
+    AUG launch alone (U ready), both launches, and the base-only dense call."""
+    for (d, r, n) in [(768, 16, 4)]:
+        B, T = 64, 1500
+        g = torch.Generator().manual_seed(1)
+        nbuf = 3
+        hs = [torch.randn(B, T, d, device=DEV, dtype=torch.bfloat16) for _ in range(nbuf)]
+        Wqkv = (torch.randn(3 * d, d, device=DEV) * 0.02).to(torch.bfloat16)
+        bqkv = torch.zeros(3 * d, device=DEV, dtype=torch.bfloat16)
+        A = (torch.randn(2 * n, r, d, device=DEV) * 0.03).to(torch.bfloat16)
+        Bp = ops.pack_lora_b((torch.randn(2 * n, d, r, device=DEV) * 0.02).to(torch.bfloat16))
+        ia = torch.randint(0, n, (B,), generator=g).to(torch.int32).to(DEV)
+        gw = torch.ones(d, device=DEV, dtype=torch.bfloat16); gb = torch.zeros(d, device=DEV, dtype=torch.bfloat16)
+        it = [0]
+
+        def nxt():
+            it[0] += 1
+            return it[0] % nbuf
+        fl = 2.0 * B * T * d * 3 * d + 2.0 * B * T * r * 4 * d
+        ms = timeit(lambda: ops.layernorm_fwd(hs[nxt()], gw, gb, 1e-5))
+        log(f"[lnu] d={d} layernorm: {ms*1e3:.1f} us  {4.0*B*T*d/ms/1e6:.0f} GB/s")
+        ms = timeit(lambda: ops.layernorm_lora_u_fwd(hs[nxt()], gw, gb, A, ia, 2, 2.0))
+        log(f"[lnu] d={d} r={r} layernorm + U fused: {ms*1e3:.1f} us  {(4.0*B*T*d + 4.0*B*T*r)/ms/1e6:.0f} GB/s")
+        none = torch.full((B,), -1, dtype=torch.int32, device=DEV)
+        ms = timeit(lambda: ops.layernorm_lora_u_fwd(hs[nxt()], gw, gb, A, none, 2, 2.0))
+        log(f"[lnu] d={d} r={r} fused kernel, every utterance base-only (LayerNorm part alone): {ms*1e3:.1f} us")
+        ms = timeit(lambda: ops.lora_u_fwd(hs[nxt()], A, ia, 2, 2.0, d))
+        log(f"[lnu] d={d} r={r} tcgen05 U pass alone: {ms*1e3:.1f} us  {2.0*B*T*d/ms/1e6:.0f} GB/s")
+        x, u = ops.layernorm_lora_u_fwd(hs[0], gw, gb, A, ia, 2, 2.0)
+        ms = timeit(lambda: ops.attn_proj_fwd(hs[nxt()], Wqkv, bqkv, A, Bp, ia, [0, -1, 1], [1, 1, 1], 2, 2.0, u=u))
+        log(f"[lnu] d={d} r={r} q|k|v dense launch alone (U ready): {ms*1e3:.1f} us  {fl/ms/1e9:.0f} TFLOP/s")
+        ms = timeit(lambda: ops.attn_proj_fwd(hs[nxt()], Wqkv, bqkv, A, Bp, ia, [0, -1, 1], [1, 1, 1], 2, 2.0, split=True))
+        log(f"[lnu] d={d} r={r} q|k|v U pass + dense launch: {ms*1e3:.1f} us  {fl/ms/1e9:.0f} TFLOP/s")
+        ms = timeit(lambda: ops.attn_proj_fwd(hs[nxt()], Wqkv, bqkv, None, None, None, [-1, -1, -1], [1, 1, 1], 1, 2.0))
+        log(f"[lnu] d={d} q|k|v base only: {ms*1e3:.1f} us  {2.0*B*T*d*3*d/ms/1e9:.0f} TFLOP/s")
+    return True
+
+
+def suite_l2chunk():
+    """Does running LayerNorm -> U pass -> dense launch per utterance CHUNK keep x in L2 (126 MB) between the three reads?
+    Times LN + q|k|v+LoRA over the 64-clip batch in 1 / 2 / 4 chunks."""
+    d, r, n, B, T = 768, 16, 4, 64, 1500
+    g = torch.Generator().manual_seed(1)
+    hs = [torch.randn(B, T, d, device=DEV, dtype=torch.bfloat16) for _ in range(3)]
+    Wqkv = (torch.randn(3 * d, d, device=DEV) * 0.02).to(torch.bfloat16)
+    bqkv = torch.zeros(3 * d, device=DEV, dtype=torch.bfloat16)
+    A = (torch.randn(2 * n, r, d, device=DEV) * 0.03).to(torch.bfloat16)
+    Bp = ops.pack_lora_b((torch.randn(2 * n, d, r, device=DEV) * 0.02).to(torch.bfloat16))
+    ia = torch.randint(0, n, (B,), generator=g).to(torch.int32).to(DEV)
+    gw = torch.ones(d, device=DEV, dtype=torch.bfloat16); gb = torch.zeros(d, device=DEV, dtype=torch.bfloat16)
+    it = [0]
+    for nchunk in (1, 2, 4, 8):
+        c = B // nchunk
+
+        def f():
+            it[0] += 1
+            h = hs[it[0] % 3]
+            for i in range(nchunk):
+                x = ops.layernorm_fwd(h[i * c:(i + 1) * c], gw, gb, 1e-5)
+                ops.attn_proj_fwd(x, Wqkv, bqkv, A, Bp, ia[i * c:(i + 1) * c].contiguous(), [0, -1, 1], [1, 1, 1], 2, 2.0, split=True)
+        ms = timeit(f)
+        log(f"[l2chunk] LN + q|k|v+LoRA (U pass + dense), {nchunk} chunk(s) of {c} clips: {ms*1e3:.1f} us")
+    return True
+
+
 if __name__ == "__main__":
     suites = sys.argv[1:] or ["k2", "k1", "rows", "k3", "perf"]
     t0 = time.time()
