@@ -19,6 +19,7 @@ constexpr int K3_COLS = 128;        // columns of x / dy per CTA
 constexpr int K3_SUB = 64;          // rows per pipeline sub-tile
 constexpr int K3_CHUNK_ROWS = 512;  // rows per CTA (within one utterance)
 constexpr int K3_QPITCH = K3_COLS * 2 + 16;  // bytes, padded against ldmatrix bank conflicts
+constexpr int64_t K3_SPLIT_MIN_ROWS = 4096;  // dx: split LoRA path from this many rows up (as ops.SPLIT_MIN_ROWS forward)
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool pred) {
   const int sz = pred ? 16 : 0;  // src-size 0 -> zero fill
@@ -202,13 +203,29 @@ int k3_qv_lora_bwd(const K3Args& a, cudaStream_t stream) {
   ws += align256(static_cast<int64_t>(chunks) * a.r * dmax * 4);
   float* partB = reinterpret_cast<float*>(ws);
 
-  // dx (+ v = scale·dy·B_k saved as the "u" of the transposed problem)
+  // dx (+ v = scale·dy·B_k saved as the "u" of the transposed problem): K1 on transposed operands.
+  //   * dx == NULL (the input needs no gradient: first encoder layer): only v is needed -> the U pass alone, no d x d GEMM;
+  //   * >= K3_SPLIT_MIN_ROWS rows: the split path (U pass -> v, then the dense 256-wide kernel with the low-rank term as
+  //     one extra K block): the single-launch LoRA kernel is limited to 128/192-wide tiles by its TMEM budget
+  //     (ncu: 52 % vs 74 % tensor-active at M = 96 000);
+  //   * fewer rows: the single-launch kernel (one launch is cheaper than two below ~4 k rows).
   K1Args k1{};
   k1.x = a.dy; k1.W = a.Wt; k1.bias = nullptr; k1.A_stack = a.Bt_stack; k1.Bp_stack = a.At_stack;
   k1.utt_adapter = a.utt_adapter; k1.y = a.dx ? a.dx : dx_scratch; k1.u_out = v;
   k1.B = a.B; k1.T = a.T; k1.d_in = a.d_out; k1.d_out = a.d_in; k1.r = a.r; k1.n_adapters = a.n_adapters;
   k1.scale = a.scale;
-  int rc = k1_qv_lora_fwd(k1, stream);
+  int rc;
+  const bool pair_ok = a.d_out % 64 == 0 && a.d_in % 128 == 0;
+  if (pair_ok && (!a.dx || rows >= K3_SPLIT_MIN_ROWS)) {
+    k1.u_ws = v;                       // [1][B, T, r] == the [B*T, r] layout the skinny kernel reads
+    k1.u_out = nullptr;
+    k1.n_sets = 1;
+    k1.u_phase = a.dx ? 0 : 1;
+    int bn = (a.d_in % 256 == 0) ? 256 : ((a.d_in % 192 == 0) ? 192 : 128);
+    rc = k1v2_qv_lora_fwd(k1, bn, stream);
+  } else {
+    rc = k1_qv_lora_fwd(k1, stream);
+  }
   if (rc) return rc;
 
   K3SkinnyParams sp{};

@@ -55,14 +55,20 @@ class FlatGradBucket:
         total = sum(p.numel() for p in ps)
         self.buffer = torch.zeros(total, dtype=torch.float32, device=dev)
         self.views: List[torch.Tensor] = []
+        self._offsets: List[int] = []
         off = 0
         for p in ps:
             if p.dtype != torch.float32:
                 raise TypeError("FlatGradBucket expects fp32 LoRA parameters (PEFT keeps adapters in fp32)")
             v = self.buffer[off: off + p.numel()].view_as(p)
             p.grad = v
+            p._sar_direct_grad = True      # lora_linear._QVLoRAFn: K3 may accumulate into this slice in place
             self.views.append(v)
+            self._offsets.append(off)
             off += p.numel()
+        self._offsets.append(off)
+        self._index = {id(p): i for i, p in enumerate(ps)}
+        self._overlap = None
 
     def attach(self) -> int:
         """Re-point every ``param.grad`` at its bucket view; returns how many had been detached.  An optimizer's
@@ -78,6 +84,29 @@ class FlatGradBucket:
     def zero_(self) -> None:
         self.buffer.zero_()
         self.attach()
+        if self._overlap is not None:
+            self._overlap.reset()
+
+    # ---- all-reduce overlapped with backward -----------------------------------------------------------------------
+    def enable_overlap(self, n_chunks: int = 4, group=None) -> None:
+        """Split the bucket into ``n_chunks`` contiguous chunks (at parameter boundaries, ~equal bytes).  As soon as every
+        gradient of a chunk has landed during backward — the bucket is in backward order, so chunks complete front to
+        back — the chunk's all-reduce is launched on a side stream behind an event, while backward continues on the
+        compute stream (src/training/trainer.py:251-277 semantics are kept: call ``finish_overlap()`` before the clip).
+        Call ``zero_()`` at the start of every step."""
+        self._overlap = _OverlappedAllReduce(self, n_chunks, group)
+
+    def set_overlap_enabled(self, enabled: bool) -> None:
+        """Switch the chunk all-reduces off / on (e.g. for a local reference step) without removing the hooks."""
+        if self._overlap is not None:
+            self._overlap.enabled = bool(enabled)
+
+    def finish_overlap(self) -> None:
+        """Wait for the chunk all-reduces (launching any chunk that never completed) and scale by 1/world."""
+        if self._overlap is None:
+            raise RuntimeError("enable_overlap() was not called")
+        self.check_attached()
+        self._overlap.finish()
 
     def check_attached(self) -> None:
         """Raise if any gradient lives outside the bucket (``zero_grad(set_to_none=True)`` ran after ``zero_()``)."""
@@ -112,3 +141,83 @@ class FlatGradBucket:
         coef = torch.clamp(max_norm / (total + 1e-6), max=1.0)
         self.buffer.mul_(coef)
         return total
+
+
+class _OverlappedAllReduce:
+    def __init__(self, bucket: FlatGradBucket, n_chunks: int, group):
+        self.b, self.group = bucket, group
+        total = bucket.buffer.numel()
+        n_chunks = max(1, min(n_chunks, len(bucket.params)))
+        bounds, target = [0], total / n_chunks
+        for i in range(len(bucket.params)):
+            end = bucket._offsets[i + 1]
+            if end >= target * len(bounds) and len(bounds) < n_chunks:
+                bounds.append(i + 1)
+        if bounds[-1] != len(bucket.params):
+            bounds.append(len(bucket.params))
+        self.param_bounds = bounds                      # chunk c = params [bounds[c], bounds[c+1])
+        self.chunk_of = [0] * len(bucket.params)
+        for c in range(len(bounds) - 1):
+            for i in range(bounds[c], bounds[c + 1]):
+                self.chunk_of[i] = c
+        self.side = torch.cuda.Stream(device=bucket.buffer.device) if bucket.buffer.is_cuda else None
+        self.works: List = []
+        self.launched: List[bool] = []
+        self.pending: List[int] = []
+        self.enabled = True
+        self.reset()
+        from . import lora_linear
+
+        lora_linear.GRAD_READY_LISTENERS.append(self._ready)          # gradients K3 wrote in place
+        for p in bucket.params:                                       # gradients autograd accumulated
+            p.register_post_accumulate_grad_hook(lambda q: self._ready((q,)))
+
+    def reset(self) -> None:
+        n = len(self.param_bounds) - 1
+        self.pending = [self.param_bounds[c + 1] - self.param_bounds[c] for c in range(n)]
+        self.launched = [False] * n
+        self.seen = set()
+        self.works = []
+
+    def _active(self) -> bool:
+        return self.enabled and dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def _ready(self, params) -> None:
+        for p in params:
+            i = self.b._index.get(id(p))
+            if i is None or i in self.seen:
+                continue
+            self.seen.add(i)
+            c = self.chunk_of[i]
+            self.pending[c] -= 1
+            if self.pending[c] == 0:
+                self._launch(c)
+
+    def _launch(self, c: int) -> None:
+        if self.launched[c]:
+            return
+        self.launched[c] = True
+        if not self._active():
+            return
+        s, e = self.b._offsets[self.param_bounds[c]], self.b._offsets[self.param_bounds[c + 1]]
+        view = self.b.buffer[s:e]
+        if self.side is not None:
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(view.device))     # everything queued so far: this chunk's K3 launches
+            self.side.wait_event(ev)
+            with torch.cuda.stream(self.side):
+                dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group)
+        else:
+            self.works.append(dist.all_reduce(view, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def finish(self) -> None:
+        for c in range(len(self.launched)):
+            if not self.launched[c]:
+                self._launch(c)
+        if not self._active():
+            return
+        if self.side is not None:
+            torch.cuda.current_stream(self.b.buffer.device).wait_stream(self.side)
+        for w in self.works:
+            w.wait()
+        self.b.buffer.div_(dist.get_world_size(self.group))

@@ -40,12 +40,31 @@ class _QVLoRAFn(torch.autograd.Function):
         m: "RoutedLoRALinear" = ctx.module
         st = m._stacks(backward=True)
         n, rp = st["A"].shape[0], st["A"].shape[1]
-        dA = torch.zeros(n, rp, m.in_features, dtype=torch.float32, device=x.device)
-        dB = torch.zeros(n, m.out_features, rp, dtype=torch.float32, device=x.device)
+        names = m.adapter_order
+        # Single-adapter training (the reference trainer's case) under dist.FlatGradBucket: K3 accumulates STRAIGHT into
+        # the parameters' ``.grad`` tensors, which are slices of the flat NCCL bucket — the gradient never exists anywhere
+        # else ("accumulating into caller-provided offsets of one flat bucket").  Opt-in per parameter
+        # (``_sar_direct_grad``, set by the bucket): plain ``torch.autograd.grad`` users keep autograd's semantics.
+        direct = None
+        if n == 1 and m.r[names[0]] == rp and st["grad_a_gain"][0] == 1.0 and st["grad_b_gain"][0] == 1.0:
+            wA, wB = m.lora_A[names[0]].weight, m.lora_B[names[0]].weight
+            gA, gB = wA.grad, wB.grad
+            if (getattr(wA, "_sar_direct_grad", False) and getattr(wB, "_sar_direct_grad", False)
+                    and wA.requires_grad and wB.requires_grad and gA is not None and gB is not None
+                    and gA.dtype == torch.float32 and gB.dtype == torch.float32 and gA.is_contiguous()
+                    and gB.is_contiguous() and gA.device == x.device and not gA.requires_grad and not gB.requires_grad):
+                direct = (gA.view(1, rp, m.in_features), gB.view(1, m.out_features, rp))
+        if direct is not None:
+            dA, dB = direct
+        else:
+            dA = torch.zeros(n, rp, m.in_features, dtype=torch.float32, device=x.device)
+            dB = torch.zeros(n, m.out_features, rp, dtype=torch.float32, device=x.device)
         dx = ops.qv_lora_bwd(dy.to(torch.bfloat16), x, u, st["Wt"], st["At"], st["Bt"], utt_adapter, dA, dB,
                              st["scale"], need_dx=ctx.needs_input_grad[0])
+        if direct is not None:
+            _notify_grad_ready(m.lora_A[names[0]].weight, m.lora_B[names[0]].weight)
+            return (dx, None, None, None, None)          # the gradients are already in place
         grads: List[Optional[torch.Tensor]] = []
-        names = m.adapter_order
         for k, name in enumerate(names):        # lora_A weights, in stack order
             w = m.lora_A[name].weight
             grads.append((dA[k, : m.r[name]] * st["grad_a_gain"][k]).to(w.dtype) if w.requires_grad else None)
@@ -53,6 +72,16 @@ class _QVLoRAFn(torch.autograd.Function):
             w = m.lora_B[name].weight
             grads.append((dB[k, :, : m.r[name]] * st["grad_b_gain"][k]).to(w.dtype) if w.requires_grad else None)
         return (dx, None, None, *grads)
+
+
+# Parameters whose gradient K3 wrote in place tell whoever registered here (dist.FlatGradBucket's overlapped all-reduce):
+# autograd's AccumulateGrad — and with it every post-accumulate hook — never runs for them.
+GRAD_READY_LISTENERS: List = []
+
+
+def _notify_grad_ready(*params) -> None:
+    for fn in GRAD_READY_LISTENERS:
+        fn(params)
 
 
 class RoutedLoRALinear(nn.Module):

@@ -108,3 +108,51 @@ def test_two_rank_gloo_allreduced_grads_equal_single_process_grads():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert sorted(results) == [(0, True), (1, True)]
+
+
+def _overlap_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        ps = [torch.nn.Parameter(torch.randn(3, 4)) for _ in range(6)]          # a 6-"layer" chain, bucket in backward order
+        bucket = FlatGradBucket(ps)
+        bucket.enable_overlap(n_chunks=3)
+        assert bucket._overlap.param_bounds == [0, 2, 4, 6]
+        g = torch.Generator().manual_seed(1)
+        x = torch.randn(4, 4, generator=g)
+        xs = shard_batch(x)
+        ok = True
+        for step in range(2):                                                    # second step: reset() re-arms the chunks
+            bucket.zero_()
+            h = xs
+            for p_ in ps:
+                h = torch.tanh(h @ p_.t() @ p_)
+            (h.pow(2).sum() / 4 * world).backward()
+            assert all(bucket._overlap.launched)                                 # every chunk went out DURING backward
+            bucket.finish_overlap()
+            refs = [p_.detach().clone().requires_grad_(True) for p_ in ps]
+            h = x
+            for r_ in refs:
+                h = torch.tanh(h @ r_.t() @ r_)
+            (h.pow(2).sum() / 4).backward()
+            ok = ok and all(torch.allclose(p_.grad, r_.grad, atol=1e-5) for p_, r_ in zip(ps, refs))
+        q.put((rank, bool(ok)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_overlapped_chunked_allreduce_matches_single_process_grads():
+    """FlatGradBucket.enable_overlap: chunks are all-reduced as soon as their gradients land (hooks fire during
+    backward), results equal the single-process gradients of the global batch."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_overlap_worker, args=(r, world, port, q)) for r in range(world)]
+    for p_ in procs:
+        p_.start()
+    results = [q.get(timeout=120) for _ in range(world)]
+    for p_ in procs:
+        p_.join(timeout=60)
+    assert sorted(results) == [(0, True), (1, True)]
