@@ -299,6 +299,20 @@ int sar_router_fwd(const void* h, int h_is_fp32, const float* ln_w, const float*
                    int32_t* seg_starts_out, void* ws, void* stream);
 
 /*
+ * K2 with the encoder's final LayerNorm folded in: h_pre is the last encoder layer's residual stream
+ * (bf16 [B, T, d]) BEFORE WhisperEncoder.layer_norm ($HF/modeling_whisper.py:643); the kernel applies that LayerNorm
+ * (enc_ln_w / enc_ln_b bf16 [d], result rounded to bf16 exactly like the stored encoder output), then the LID head's
+ * LayerNorm and the mean over T (src/models/adapter_router.py:268, :229) — one read of h_pre instead of LayerNorm
+ * write + K2 read of the [B, 1500, d] encoder output.  Everything else as sar_router_fwd.
+ */
+int sar_router_fwd_fused_ln(const void* h_pre, const void* enc_ln_w, const void* enc_ln_b, float enc_ln_eps,
+                            const float* ln_w, const float* ln_b, const float* W1, const float* b1, const float* g1,
+                            const float* be1, const float* W2, const float* b2, const float* g2, const float* be2,
+                            const float* W3, const float* b3, int B, int T, int d, int h1, int h2, int C,
+                            float* logits_out, float* probs_out, int32_t* idx_out, int32_t* perm_out,
+                            int32_t* seg_starts_out, void* ws, void* stream);
+
+/*
  * K3 — LoRA-only backward of K1 (base W frozen):
  *   dx      = dy·W + (scale·dy·B_k)·A_k                (skipped when dx == NULL)
  *   dA_k   += scale · (dy·B_k)ᵀ · x      fp32 [n_adapters, r, d_in]

@@ -44,6 +44,7 @@ _SIGNATURES = {
     "sar_layernorm_lora_u_supported": (c_int, [c_int] * 3),
     "sar_qv_lora_fwd_rows": (c_int, [c_void_p] * 5 + [c_void_p, c_void_p] + [c_int] * 5 + [c_float, c_void_p, c_void_p]),
     "sar_router_fwd": (c_int, [c_void_p, c_int] + [c_void_p] * 12 + [c_int] * 6 + [c_void_p] * 5 + [c_void_p, c_void_p]),
+    "sar_router_fwd_fused_ln": (c_int, [c_void_p, c_void_p, c_void_p, c_float] + [c_void_p] * 12 + [c_int] * 6 + [c_void_p] * 5 + [c_void_p, c_void_p]),
     "sar_qv_lora_bwd": (c_int, [c_void_p] * 7 + [c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 6 + [c_float, c_void_p, c_void_p]),
 }
 

@@ -20,6 +20,9 @@ namespace sar {
 constexpr int K2_THREADS = 256;
 constexpr int K2_WARPS = K2_THREADS / 32;
 constexpr float K2_EPS = 1e-5f;
+#ifndef K2_FR_PLAIN
+#define K2_FR_PLAIN 2
+#endif
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
@@ -249,8 +252,223 @@ k2_pool_kernel(const void* __restrict__ h, float* __restrict__ partial, int* __r
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// k2_pool2 — the bf16 pooling pass, second generation (and, with PRE_LN, the fusion SURVEY §8(f)-4 asks for: encoder
+// final LayerNorm -> LID LayerNorm -> mean over T straight from the last encoder layer's residual stream, so the LID
+// pass never writes and re-reads the [B, 1500, d] encoder output; reference: $HF/modeling_whisper.py:643 +
+// src/models/adapter_router.py:268, :229).
+//
+// The ring version above ran at 3.1 TB/s (47 % of the measured HBM peak): ncu showed its 8 consumer warps per CTA
+// stalled on their own statistic chains.  What the plain LayerNorm kernel (5.6 TB/s) has and the ring did not is
+// OCCUPANCY with cheap rows: here a warp owns a frame, loads it straight into 12 registers (d = 768; 16-byte
+// lane-strided loads, full 128-byte lines per request), two frames per warp in flight, all arithmetic on the packed
+// fp32 pipe (add / fma .f32x2: one instruction per bf16 pair — ~130 instructions per frame instead of ~350), 16
+// warps per SM.  Per-lane accumulators, fixed-order cross-warp reduction, fixed-order partials: deterministic.
+__device__ __forceinline__ float2 k2_unpack2(uint32_t w) {
+  return make_float2(__uint_as_float(w << 16), __uint_as_float(w & 0xFFFF0000u));
+}
+__device__ __forceinline__ float2 k2_fadd2(float2 a, float2 b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<uint64_t*>(&a)), "l"(*reinterpret_cast<uint64_t*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 k2_fmul2(float2 a, float2 b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<uint64_t*>(&a)), "l"(*reinterpret_cast<uint64_t*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 k2_ffma2(float2 a, float2 b, float2 c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(d)
+      : "l"(*reinterpret_cast<uint64_t*>(&a)), "l"(*reinterpret_cast<uint64_t*>(&b)), "l"(*reinterpret_cast<uint64_t*>(&c)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ uint32_t k2_pack2(float2 v) {
+  __nv_bfloat162 t = __floats2bfloat162_rn(v.x, v.y);
+  return *reinterpret_cast<uint32_t*>(&t);
+}
+
+template <int NV, bool PRE_LN>
+__global__ void __launch_bounds__(K2_THREADS, 2)
+k2_pool2_kernel(const uint4* __restrict__ h, const uint4* __restrict__ g1, const uint4* __restrict__ b1, float eps1,
+                float* __restrict__ partial, int* __restrict__ done_counter, int T, int nvec, float inv_d,
+                int rows_per_chunk) {
+  extern __shared__ __align__(16) float k2_red[];                 // [K2_WARPS][nvec * 8]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.y, chunk = blockIdx.x;
+  if (blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) *done_counter = 0;
+  const int t0 = chunk * rows_per_chunk;
+  const int t1 = min(T, t0 + rows_per_chunk);
+  const int d = nvec * 8;
+  uint4 gq[PRE_LN ? NV : 1], bq[PRE_LN ? NV : 1];
+  if constexpr (PRE_LN) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int c = lane + 32 * i;
+      gq[i] = c < nvec ? __ldg(g1 + c) : make_uint4(0u, 0u, 0u, 0u);
+      bq[i] = c < nvec ? __ldg(b1 + c) : make_uint4(0u, 0u, 0u, 0u);
+    }
+  }
+  float2 acc[NV][4];
+#pragma unroll
+  for (int i = 0; i < NV; ++i)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[i][e] = make_float2(0.f, 0.f);
+  const uint4* base = h + static_cast<size_t>(b) * T * nvec;
+
+  // FR frames per warp are processed in LOCKSTEP: their statistic chains (a serial packed-fp32 sum and a 5-step shuffle
+  // reduction, twice per LayerNorm) are independent, so the scheduler interleaves them.  Processing the frames one after
+  // the other — whatever number of loads was in flight — left a warp issuing one instruction per ~8 cycles and the pass
+  // at 3.4 TB/s (ncu: warps active 21 %, issue-active 38-41 %).  d <= 768 rows are 12 registers per frame: four at a
+  // time; with the encoder LayerNorm's gamma / beta resident two; wider rows one.
+  constexpr int FR = (NV <= 3) ? (PRE_LN ? 1 : K2_FR_PLAIN) : 1;
+  // mean and 1/sqrt(var + eps) of FR frames held as packed bf16 pairs (two-pass, fp32)
+  auto stats = [&](const uint4 (&v)[FR][NV], float eps, float2 (&nm)[FR], float2 (&rs)[FR]) {
+    float2 sum[FR];
+#pragma unroll
+    for (int u = 0; u < FR; ++u) sum[u] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {          // lanes past the row hold zeros: they add nothing
+#pragma unroll
+      for (int u = 0; u < FR; ++u) {
+        sum[u] = k2_fadd2(sum[u], k2_unpack2(v[u][i].x));
+        sum[u] = k2_fadd2(sum[u], k2_unpack2(v[u][i].y));
+        sum[u] = k2_fadd2(sum[u], k2_unpack2(v[u][i].z));
+        sum[u] = k2_fadd2(sum[u], k2_unpack2(v[u][i].w));
+      }
+    }
+    float m[FR];
+#pragma unroll
+    for (int u = 0; u < FR; ++u) m[u] = sum[u].x + sum[u].y;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < FR; ++u) m[u] += __shfl_xor_sync(0xffffffffu, m[u], o);
+    float2 q[FR];
+#pragma unroll
+    for (int u = 0; u < FR; ++u) {
+      nm[u] = make_float2(-m[u] * inv_d, -m[u] * inv_d);
+      q[u] = make_float2(0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (lane + 32 * i < nvec) {
+#pragma unroll
+        for (int u = 0; u < FR; ++u) {
+          float2 t;
+          t = k2_fadd2(k2_unpack2(v[u][i].x), nm[u]); q[u] = k2_ffma2(t, t, q[u]);
+          t = k2_fadd2(k2_unpack2(v[u][i].y), nm[u]); q[u] = k2_ffma2(t, t, q[u]);
+          t = k2_fadd2(k2_unpack2(v[u][i].z), nm[u]); q[u] = k2_ffma2(t, t, q[u]);
+          t = k2_fadd2(k2_unpack2(v[u][i].w), nm[u]); q[u] = k2_ffma2(t, t, q[u]);
+        }
+      }
+    }
+    float qs[FR];
+#pragma unroll
+    for (int u = 0; u < FR; ++u) qs[u] = q[u].x + q[u].y;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+      for (int u = 0; u < FR; ++u) qs[u] += __shfl_xor_sync(0xffffffffu, qs[u], o);
+#pragma unroll
+    for (int u = 0; u < FR; ++u) {
+      const float rstd = 1.0f / sqrtf(qs[u] * inv_d + eps);
+      rs[u] = make_float2(rstd, rstd);
+    }
+  };
+
+  // register double buffering: the loads of the NEXT group of FR frames are issued before this group is reduced, so a
+  // warp always has a group in flight (without it a warp alternated between waiting ~2 us for its loads and ~450
+  // instructions of arithmetic, and 3-4 such warps per scheduler did not keep HBM busy)
+  auto load_group = [&](int t, uint4 (&v)[FR][NV]) {
+#pragma unroll
+    for (int u = 0; u < FR; ++u) {
+      const int tu = t + u * K2_WARPS;
+      const uint4* r = base + static_cast<size_t>(tu < t1 ? tu : t0) * nvec;   // dead slot: any valid frame, weight 0
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        const int c = lane + 32 * i;
+        v[u][i] = c < nvec ? __ldcs(r + c) : make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+  };
+  uint4 vn[FR][NV];
+  if (t0 + warp < t1) load_group(t0 + warp, vn);
+#pragma unroll 1
+  for (int t = t0 + warp; t < t1; t += FR * K2_WARPS) {
+    uint4 v[FR][NV];
+    bool live[FR];
+#pragma unroll
+    for (int u = 0; u < FR; ++u) {
+      live[u] = t + u * K2_WARPS < t1;                     // warp-uniform
+#pragma unroll
+      for (int i = 0; i < NV; ++i) v[u][i] = vn[u][i];
+    }
+    if (t + FR * K2_WARPS < t1) load_group(t + FR * K2_WARPS, vn);
+    float2 nm[FR], rs[FR];
+    if constexpr (PRE_LN) {
+      // the encoder's final LayerNorm: y = bf16((x - mean) * rstd * gamma + beta) — exactly the tensor the unfused
+      // path would have written (sar_layernorm_fwd) and this kernel would have read back
+      stats(v, eps1, nm, rs);
+#pragma unroll
+      for (int i = 0; i < NV; ++i) {
+        if (lane + 32 * i < nvec) {
+#pragma unroll
+          for (int u = 0; u < FR; ++u) {
+            v[u][i].x = k2_pack2(k2_ffma2(k2_fmul2(k2_fadd2(k2_unpack2(v[u][i].x), nm[u]), rs[u]), k2_unpack2(gq[i].x), k2_unpack2(bq[i].x)));
+            v[u][i].y = k2_pack2(k2_ffma2(k2_fmul2(k2_fadd2(k2_unpack2(v[u][i].y), nm[u]), rs[u]), k2_unpack2(gq[i].y), k2_unpack2(bq[i].y)));
+            v[u][i].z = k2_pack2(k2_ffma2(k2_fmul2(k2_fadd2(k2_unpack2(v[u][i].z), nm[u]), rs[u]), k2_unpack2(gq[i].z), k2_unpack2(bq[i].z)));
+            v[u][i].w = k2_pack2(k2_ffma2(k2_fmul2(k2_fadd2(k2_unpack2(v[u][i].w), nm[u]), rs[u]), k2_unpack2(gq[i].w), k2_unpack2(bq[i].w)));
+          }
+        }
+      }
+    }
+    stats(v, K2_EPS, nm, rs);               // the LID head's LayerNorm (affine applied once per utterance, in the head)
+#pragma unroll
+    for (int u = 0; u < FR; ++u)
+      if (!live[u]) rs[u] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      if (lane + 32 * i < nvec) {
+#pragma unroll
+        for (int u = 0; u < FR; ++u) {
+          acc[i][0] = k2_ffma2(k2_fadd2(k2_unpack2(v[u][i].x), nm[u]), rs[u], acc[i][0]);
+          acc[i][1] = k2_ffma2(k2_fadd2(k2_unpack2(v[u][i].y), nm[u]), rs[u], acc[i][1]);
+          acc[i][2] = k2_ffma2(k2_fadd2(k2_unpack2(v[u][i].z), nm[u]), rs[u], acc[i][2]);
+          acc[i][3] = k2_ffma2(k2_fadd2(k2_unpack2(v[u][i].w), nm[u]), rs[u], acc[i][3]);
+        }
+      }
+    }
+  }
+
+  // fixed-order cross-warp reduction
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int e = (lane + 32 * i) * 8;
+    if (e < d) {
+      float4* dst = reinterpret_cast<float4*>(k2_red + warp * d + e);
+      dst[0] = make_float4(acc[i][0].x, acc[i][0].y, acc[i][1].x, acc[i][1].y);
+      dst[1] = make_float4(acc[i][2].x, acc[i][2].y, acc[i][3].x, acc[i][3].y);
+    }
+  }
+  __syncthreads();
+  float* out = partial + (static_cast<size_t>(b) * gridDim.x + chunk) * d;
+  for (int j = threadIdx.x; j < d; j += K2_THREADS) {
+    float sacc = 0.f;
+#pragma unroll
+    for (int w = 0; w < K2_WARPS; ++w) sacc += k2_red[w * d + j];
+    out[j] = sacc;
+  }
+}
+
+// The head is latency-bound (one CTA per utterance walks W1 [h1, d] fp32 through L2): 32 warps per CTA put four times as
+// many independent row pairs in flight as 8 did (48 us -> see DESIGN.md §4).
+constexpr int K2H_THREADS = 1024;
+constexpr int K2H_WARPS = K2H_THREADS / 32;
+
 __device__ __forceinline__ float block_sum(float v, float* scratch) {
-  // scratch: K2_WARPS floats.  All threads receive the same fixed-order sum.
+  // scratch: K2H_WARPS floats.  All threads receive the same fixed-order sum.
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   v = warp_sum(v);
   __syncthreads();
@@ -258,7 +476,7 @@ __device__ __forceinline__ float block_sum(float v, float* scratch) {
   __syncthreads();
   float s = 0.f;
 #pragma unroll
-  for (int w = 0; w < K2_WARPS; ++w) s += scratch[w];
+  for (int w = 0; w < K2H_WARPS; ++w) s += scratch[w];
   return s;
 }
 
@@ -270,7 +488,7 @@ __device__ __forceinline__ void dense_rows(const float* __restrict__ W, const fl
   if ((n_in & 3) == 0 && (reinterpret_cast<uintptr_t>(W) & 15) == 0) {
     const int n4 = n_in >> 2;
     const float4* x4 = reinterpret_cast<const float4*>(x);
-    for (int o = 2 * warp; o < n_out; o += 2 * K2_WARPS) {
+    for (int o = 2 * warp; o < n_out; o += 2 * K2H_WARPS) {
       const bool two = (o + 1) < n_out;
       const float4* w0 = reinterpret_cast<const float4*>(W + static_cast<size_t>(o) * n_in);
       const float4* w1 = reinterpret_cast<const float4*>(W + static_cast<size_t>(two ? o + 1 : o) * n_in);
@@ -302,7 +520,7 @@ __device__ __forceinline__ void dense_rows(const float* __restrict__ W, const fl
       }
     }
   } else {
-    for (int o = warp; o < n_out; o += K2_WARPS) {
+    for (int o = warp; o < n_out; o += K2H_WARPS) {
       const float* w = W + static_cast<size_t>(o) * n_in;
       float s = 0.f;
       for (int j = lane; j < n_in; j += 32) s += __ldg(w + j) * x[j];
@@ -316,15 +534,15 @@ __device__ __forceinline__ void dense_rows(const float* __restrict__ W, const fl
 __device__ __forceinline__ void ln_relu(float* v, const float* __restrict__ g, const float* __restrict__ be, int n,
                                         float* scratch) {
   float s = 0.f;
-  for (int j = threadIdx.x; j < n; j += K2_THREADS) s += v[j];
+  for (int j = threadIdx.x; j < n; j += K2H_THREADS) s += v[j];
   const float mean = block_sum(s, scratch) / static_cast<float>(n);
   float q = 0.f;
-  for (int j = threadIdx.x; j < n; j += K2_THREADS) {
+  for (int j = threadIdx.x; j < n; j += K2H_THREADS) {
     const float dlt = v[j] - mean;
     q += dlt * dlt;
   }
   const float rstd = 1.0f / sqrtf(block_sum(q, scratch) / static_cast<float>(n) + K2_EPS);
-  for (int j = threadIdx.x; j < n; j += K2_THREADS) {
+  for (int j = threadIdx.x; j < n; j += K2H_THREADS) {
     const float y = (v[j] - mean) * rstd * __ldg(g + j) + __ldg(be + j);
     v[j] = y > 0.f ? y : 0.f;
   }
@@ -344,8 +562,8 @@ struct K2HeadParams {
   int* done_counter;
 };
 
-__global__ void __launch_bounds__(K2_THREADS) k2_head_kernel(const K2HeadParams p) {
-  extern __shared__ __align__(16) float sm[];  // pooled[d] | a1[h1] | a2[h2] | lg[64] | scratch[K2_WARPS] | counts
+__global__ void __launch_bounds__(K2H_THREADS) k2_head_kernel(const K2HeadParams p) {
+  extern __shared__ __align__(16) float sm[];  // pooled[d] | a1[h1] | a2[h2] | lg[64] | scratch[K2H_WARPS] | counts
   float* pooled = sm;
   float* a1 = pooled + ((p.d + 3) & ~3);
   float* a2 = a1 + ((p.h1 + 3) & ~3);
@@ -355,7 +573,7 @@ __global__ void __launch_bounds__(K2_THREADS) k2_head_kernel(const K2HeadParams 
   const int b = blockIdx.x;
 
   const float inv_T = 1.0f / static_cast<float>(p.T);
-  for (int j = threadIdx.x; j < p.d; j += K2_THREADS) {
+  for (int j = threadIdx.x; j < p.d; j += K2H_THREADS) {
     const float* src = p.partial + static_cast<size_t>(b) * p.chunks * p.d + j;
     float s = 0.f;
     for (int c = 0; c < p.chunks; ++c) s += src[static_cast<size_t>(c) * p.d];
@@ -397,13 +615,13 @@ __global__ void __launch_bounds__(K2_THREADS) k2_head_kernel(const K2HeadParams 
     // Stable counting sort of the utterances by class, by the whole CTA (one thread walking idx[] through L2 cost
     // ~40 us at B = 64): for each class, a ballot-based block scan over the utterances in index order.
     __threadfence();
-    __shared__ int warp_tot[K2_WARPS];
+    __shared__ int warp_tot[K2H_WARPS];
     const volatile int32_t* vidx = p.idx;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     int running = 0;
     for (int c = 0; c < p.C; ++c) {
       if (threadIdx.x == 0) p.seg_starts[c] = running;
-      for (int i0 = 0; i0 < p.B; i0 += K2_THREADS) {
+      for (int i0 = 0; i0 < p.B; i0 += K2H_THREADS) {
         const int i = i0 + threadIdx.x;
         const bool flag = i < p.B && vidx[i] == c;
         const unsigned ballot = __ballot_sync(0xffffffffu, flag);
@@ -411,7 +629,7 @@ __global__ void __launch_bounds__(K2_THREADS) k2_head_kernel(const K2HeadParams 
         __syncthreads();
         int before = 0, total = 0;
 #pragma unroll
-        for (int w = 0; w < K2_WARPS; ++w) {
+        for (int w = 0; w < K2H_WARPS; ++w) {
           before += w < warp ? warp_tot[w] : 0;
           total += warp_tot[w];
         }
@@ -443,6 +661,28 @@ static int k2_rows_per_chunk(int B, int T, int num_sms) {
   int rows = (T + chunks - 1) / chunks;
   rows = (rows + K2_ROWS_PER_STAGE - 1) / K2_ROWS_PER_STAGE * K2_ROWS_PER_STAGE;
   if (rows < 16) rows = 16;   // workspace sizing assumes >= 16 frames per chunk
+  return rows;
+}
+
+static int k2_rows_per_chunk2(int B, int T, int num_sms) {
+  // k2_pool2: two CTAs per SM.  Pick the number of chunks per utterance (1x..4x the slot count) that fills whole waves
+  // best — B = 64 on 148 SMs: 4 chunks leave 13 % of the slots idle (256 CTAs on 296 slots), 9 chunks give 576 CTAs =
+  // 1.95 waves — preferring fewer, longer chunks on ties.
+  const int slots = num_sms * 2;
+  int best_c = 1;
+  double best_eff = 0.0;
+  const int c_lo = slots / B > 1 ? slots / B : 1, c_hi = 4 * slots / B > 1 ? 4 * slots / B : 1;
+  for (int c = c_lo; c <= c_hi; ++c) {
+    if ((T + c - 1) / c < 32) break;                       // at least 32 frames per chunk
+    const long long ctas = static_cast<long long>(B) * c;
+    const double eff = static_cast<double>(ctas) / (static_cast<double>((ctas + slots - 1) / slots) * slots);
+    if (eff > best_eff + 0.02) {
+      best_eff = eff;
+      best_c = c;
+    }
+  }
+  int rows = (T + best_c - 1) / best_c;
+  if (rows < 16) rows = 16;                                // workspace sizing assumes >= 16 frames per chunk
   return rows;
 }
 
@@ -480,6 +720,43 @@ static int k2_launch_pool(const K2Args& a, float* partial, int* counter, int chu
   return SAR_OK;
 }
 
+static int k2_launch_pool2(const K2Args& a, float* partial, int* counter, int chunks, int rpc, cudaStream_t stream) {
+  const int nvec = a.d / 8;
+  const int nv = (nvec + 31) / 32;
+  const dim3 grid(chunks, a.B);
+  const size_t smem = static_cast<size_t>(K2_WARPS) * a.d * sizeof(float);
+  const uint4* hp = static_cast<const uint4*>(a.h);
+  const uint4* gp = static_cast<const uint4*>(a.pre_ln_w);
+  const uint4* bp = static_cast<const uint4*>(a.pre_ln_b);
+  const float inv_d = 1.0f / static_cast<float>(a.d);
+  const bool pre = a.pre_ln_w != nullptr;
+  if (pre && (!a.pre_ln_b || ((reinterpret_cast<uintptr_t>(a.pre_ln_w) | reinterpret_cast<uintptr_t>(a.pre_ln_b)) & 15)))
+    return fail(SAR_EINVAL, "k2: fused encoder LayerNorm needs 16-byte aligned bf16 gamma and beta");
+#define SAR_K2P_CASE(N)                                                                                                  \
+  case N:                                                                                                                \
+    if (pre) {                                                                                                           \
+      if (smem > 48 * 1024)                                                                                              \
+        cudaFuncSetAttribute(k2_pool2_kernel<N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);          \
+      k2_pool2_kernel<N, true><<<grid, K2_THREADS, smem, stream>>>(hp, gp, bp, a.pre_ln_eps, partial, counter, a.T, nvec, \
+                                                                   inv_d, rpc);                                          \
+    } else {                                                                                                             \
+      if (smem > 48 * 1024)                                                                                              \
+        cudaFuncSetAttribute(k2_pool2_kernel<N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);         \
+      k2_pool2_kernel<N, false><<<grid, K2_THREADS, smem, stream>>>(hp, nullptr, nullptr, 0.f, partial, counter, a.T,    \
+                                                                    nvec, inv_d, rpc);                                   \
+    }                                                                                                                    \
+    break;
+  switch (nv) {
+    SAR_K2P_CASE(1) SAR_K2P_CASE(2) SAR_K2P_CASE(3) SAR_K2P_CASE(4) SAR_K2P_CASE(5) SAR_K2P_CASE(6) SAR_K2P_CASE(7)
+    SAR_K2P_CASE(8)
+    default: return fail(SAR_EINVAL, "k2: d must be <= 2048");
+  }
+#undef SAR_K2P_CASE
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail_cuda(e, "k2: pool launch");
+  return SAR_OK;
+}
+
 int k2_router_fwd(const K2Args& a, cudaStream_t stream) {
   if (!a.h || !a.ln_w || !a.ln_b || !a.W1 || !a.b1 || !a.g1 || !a.be1 || !a.W2 || !a.b2 || !a.g2 || !a.be2 ||
       !a.W3 || !a.b3 || !a.logits || !a.probs || !a.idx || !a.perm || !a.seg_starts || !a.ws)
@@ -491,12 +768,17 @@ int k2_router_fwd(const K2Args& a, cudaStream_t stream) {
   if ((reinterpret_cast<uintptr_t>(a.h) | reinterpret_cast<uintptr_t>(a.ws)) & 15)
     return fail(SAR_EINVAL, "k2: h and ws must be 16-byte aligned");
   const DeviceInfo& dev = device_info();
-  const int rpc = k2_rows_per_chunk(a.B, a.T, dev.num_sms);
+  const int rpc = a.h_is_fp32 ? k2_rows_per_chunk(a.B, a.T, dev.num_sms) : k2_rows_per_chunk2(a.B, a.T, dev.num_sms);
   const int chunks = (a.T + rpc - 1) / rpc;
   int* counter = reinterpret_cast<int*>(a.ws);
   float* partial = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(a.ws) + 256);
-  int rc = a.h_is_fp32 ? k2_launch_pool<true>(a, partial, counter, chunks, rpc, stream)
-                       : k2_launch_pool<false>(a, partial, counter, chunks, rpc, stream);
+  int rc;
+  if (a.h_is_fp32) {
+    if (a.pre_ln_w) return fail(SAR_EINVAL, "k2: the fused encoder LayerNorm needs bf16 states");
+    rc = k2_launch_pool<true>(a, partial, counter, chunks, rpc, stream);
+  } else {
+    rc = k2_launch_pool2(a, partial, counter, chunks, rpc, stream);
+  }
   if (rc) return rc;
 
   K2HeadParams p{};
@@ -506,8 +788,8 @@ int k2_router_fwd(const K2Args& a, cudaStream_t stream) {
   p.B = a.B; p.T = a.T; p.d = a.d; p.h1 = a.h1; p.h2 = a.h2; p.C = a.C;
   p.logits = a.logits; p.probs = a.probs; p.idx = a.idx; p.perm = a.perm; p.seg_starts = a.seg_starts;
   p.done_counter = counter;
-  const size_t smem = (static_cast<size_t>(a.d) + a.h1 + a.h2 + 12 + 64 + K2_WARPS + 80) * sizeof(float);
-  k2_head_kernel<<<a.B, K2_THREADS, smem, stream>>>(p);
+  const size_t smem = (static_cast<size_t>(a.d) + a.h1 + a.h2 + 12 + 64 + K2H_WARPS + 80) * sizeof(float);
+  k2_head_kernel<<<a.B, K2H_THREADS, smem, stream>>>(p);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail_cuda(e, "k2: head launch");
   return SAR_OK;

@@ -312,6 +312,26 @@ int sar_router_fwd(const void* h, int h_is_fp32, const float* ln_w, const float*
   return k2_router_fwd(a, static_cast<cudaStream_t>(stream));
 }
 
+int sar_router_fwd_fused_ln(const void* h_pre, const void* enc_ln_w, const void* enc_ln_b, float enc_ln_eps,
+                            const float* ln_w, const float* ln_b, const float* W1, const float* b1, const float* g1,
+                            const float* be1, const float* W2, const float* b2, const float* g2, const float* be2,
+                            const float* W3, const float* b3, int B, int T, int d, int h1, int h2, int C,
+                            float* logits_out, float* probs_out, int32_t* idx_out, int32_t* perm_out,
+                            int32_t* seg_starts_out, void* ws, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  if (!enc_ln_w || !enc_ln_b) return fail(SAR_EINVAL, "sar_router_fwd_fused_ln: null encoder LayerNorm parameters");
+  K2Args a{};
+  a.h = h_pre; a.h_is_fp32 = 0;
+  a.pre_ln_w = enc_ln_w; a.pre_ln_b = enc_ln_b; a.pre_ln_eps = enc_ln_eps;
+  a.ln_w = ln_w; a.ln_b = ln_b; a.W1 = W1; a.b1 = b1; a.g1 = g1; a.be1 = be1;
+  a.W2 = W2; a.b2 = b2; a.g2 = g2; a.be2 = be2; a.W3 = W3; a.b3 = b3;
+  a.B = B; a.T = T; a.d = d; a.h1 = h1; a.h2 = h2; a.C = C;
+  a.logits = logits_out; a.probs = probs_out; a.idx = idx_out; a.perm = perm_out; a.seg_starts = seg_starts_out;
+  a.ws = ws;
+  return k2_router_fwd(a, static_cast<cudaStream_t>(stream));
+}
+
 int sar_qv_lora_bwd(const void* dy, const void* x, const void* u, const void* Wt, const void* At_stack,
                     const void* Bt_stack, const void* Bp_stack, const int32_t* utt_adapter, void* dx, float* dA,
                     float* dB, int B, int T, int d_in, int d_out, int r, int n_adapters, float scale, void* ws,

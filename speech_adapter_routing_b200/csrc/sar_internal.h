@@ -103,6 +103,11 @@ struct K2Args {
   int32_t* perm;
   int32_t* seg_starts;
   void* ws;
+  // optional: h is the encoder's residual stream BEFORE its final LayerNorm; apply that LayerNorm (bf16 gamma / beta,
+  // result rounded to bf16 like the stored encoder output) on the fly.  Null = h is the encoder output itself.
+  const void* pre_ln_w;
+  const void* pre_ln_b;
+  float pre_ln_eps;
 };
 int64_t k2_workspace_bytes(int64_t B, int64_t T, int64_t d);
 int k2_router_fwd(const K2Args& a, cudaStream_t stream);

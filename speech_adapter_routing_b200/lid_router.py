@@ -27,6 +27,7 @@ from .peft_compat import LoraConfig, PeftModel, inject_lora, lora_modules
 from .routing import base_only, operand_epoch, route, route_base
 
 logger = logging.getLogger(__name__)
+FUSED_LID = __import__("os").environ.get("SAR_FUSED_LID", "1") != "0"   # LID pass ends inside K2 (A/B switch)
 
 
 class LanguageClassifier(nn.Module):
@@ -397,6 +398,28 @@ class AdapterRouter(nn.Module):
     def detect_indices(self, encoder_hidden_states: torch.Tensor) -> ops.RouterOut:
         return self.classifier.route_batch(encoder_hidden_states)
 
+    def route_inputs(self, input_features: torch.Tensor) -> ops.RouterOut:
+        """The LID pass in one go: base-weights encoder -> router head (reference :585-588).  On the fused CUDA path the
+        encoder's final LayerNorm, the LID head's LayerNorm and the mean over T all run inside K2, on the last encoder
+        layer's residual stream (sar_router_fwd_fused_ln): the [B, 1500, d] encoder output of the LID pass is never
+        written or read back.  Same results as ``detect_indices(extract_encoder_features(x))``."""
+        clf, fx = self.classifier, self.feature_extractor
+        if (FUSED_LID and input_features.is_cuda and fx.layer_index == -1 and not clf.training
+                and clf._k2_eligible(None)):
+            from .whisper_blocks import encoder_pre_ln
+
+            enc = fx._get_encoder()
+            # wider rows (d = 1024 / 1280) keep the two-step form: with gamma / beta resident the folded kernel spills
+            # at its register budget and measured slower than LayerNorm + K2 (166 vs 94 + 51 us at d = 1280, B = 64)
+            h_pre = None
+            if getattr(getattr(enc, "config", None), "d_model", 1 << 30) <= 768:
+                with torch.no_grad(), route_base():
+                    h_pre = encoder_pre_ln(enc, input_features)
+            if h_pre is not None:
+                ln = enc._sar_pack["ln"].get()
+                return ops.router_fwd(h_pre, clf._k2_params(h_pre.device), pre_ln=(ln.W, ln.b, enc.layer_norm.eps))
+        return self.detect_indices(self.extract_encoder_features(input_features))
+
     def _run(self, input_features, utt_adapter, labels=None, **kwargs):
         kw = {k: v for k, v in kwargs.items()
               if k in ("attention_mask", "decoder_input_ids", "decoder_attention_mask")}
@@ -407,8 +430,7 @@ class AdapterRouter(nn.Module):
 
     def forward(self, input_features: torch.Tensor, labels: Optional[torch.Tensor] = None,
                 **kwargs) -> Dict[str, torch.Tensor]:
-        h = self.extract_encoder_features(input_features)
-        routed = self.detect_indices(h)
+        routed = self.route_inputs(input_features)
         if self.strategy == "hard":
             return self._hard_routing(input_features, routed.idx, labels, **kwargs)
         if self.strategy == "soft":
@@ -485,7 +507,7 @@ class AdapterRouter(nn.Module):
         if language is not None:
             idx = torch.full((B,), self.lang_to_idx[language], dtype=torch.int32, device=dev)
         else:
-            idx = self.detect_indices(self.extract_encoder_features(input_features)).idx
+            idx = self.route_inputs(input_features).idx
         from .decode import greedy_decoder_for, plan_greedy
 
         native = greedy_decoder_for(self.whisper)

@@ -466,8 +466,10 @@ class RouterParams(NamedTuple):
         return RouterParams(*[sd[k].detach().to(device=device, dtype=torch.float32).contiguous() for k in keys])
 
 
-def router_fwd(h: torch.Tensor, p: RouterParams) -> RouterOut:
-    """K2: LayerNorm → mean over T → MLP → softmax → argmax → (idx, perm, seg_starts).  h is [B,T,d] bf16 or fp32."""
+def router_fwd(h: torch.Tensor, p: RouterParams, pre_ln: Optional[Tuple[torch.Tensor, torch.Tensor, float]] = None) -> RouterOut:
+    """K2: LayerNorm → mean over T → MLP → softmax → argmax → (idx, perm, seg_starts).  h is [B,T,d] bf16 or fp32.
+    ``pre_ln = (gamma, beta, eps)`` (bf16): h is the encoder's residual stream BEFORE its final LayerNorm, which the
+    kernel applies on the fly (sar_router_fwd_fused_ln)."""
     _need_cuda(h, *p)
     if h.dim() != 3:
         raise ValueError("h must be [B, T, d]")
@@ -486,8 +488,17 @@ def router_fwd(h: torch.Tensor, p: RouterParams) -> RouterOut:
     if nbytes < 0:
         check(int(nbytes))
     ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-    check(lib().sar_router_fwd(_ptr(h), int(h.dtype == torch.float32), *[_ptr(t) for t in p], B, T, d, h1, h2, C,
-                               _ptr(logits), _ptr(probs), _ptr(idx), _ptr(perm), _ptr(seg), _ptr(ws), _stream(h)))
+    if pre_ln is not None:
+        g1, b1, eps1 = pre_ln
+        if h.dtype != torch.bfloat16:
+            raise TypeError("the fused encoder LayerNorm needs bf16 states")
+        g1, b1 = _bf16c(g1, "pre_ln gamma"), _bf16c(b1, "pre_ln beta")
+        check(lib().sar_router_fwd_fused_ln(_ptr(h), _ptr(g1), _ptr(b1), float(eps1), *[_ptr(t) for t in p], B, T, d, h1,
+                                            h2, C, _ptr(logits), _ptr(probs), _ptr(idx), _ptr(perm), _ptr(seg), _ptr(ws),
+                                            _stream(h)))
+    else:
+        check(lib().sar_router_fwd(_ptr(h), int(h.dtype == torch.float32), *[_ptr(t) for t in p], B, T, d, h1, h2, C,
+                                   _ptr(logits), _ptr(probs), _ptr(idx), _ptr(perm), _ptr(seg), _ptr(ws), _stream(h)))
     LAUNCHES["k2"] += 2
     return RouterOut(logits, probs, idx, perm, seg)
 

@@ -386,17 +386,15 @@ class _EmbedPack:
         return self
 
 
-def _encoder_forward(self, input_features, attention_mask=None, **kwargs):
-    """WhisperEncoder.forward ($HF/models/whisper/modeling_whisper.py:590-647) without HF's per-call bookkeeping."""
-    x = input_features
-    fast = (FUSED_BLOCKS_ENABLED and isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.bfloat16
+def _encoder_fast_ok(self, x, kwargs) -> bool:
+    return (FUSED_BLOCKS_ENABLED and isinstance(x, torch.Tensor) and x.is_cuda and x.dtype == torch.bfloat16
             and x.dim() == 3 and not torch.is_grad_enabled() and not self.training
             and not kwargs.get("output_attentions") and not kwargs.get("output_hidden_states")
             and kwargs.get("return_dict", True) is not False)
-    if not fast:
-        return self._sar_hf_forward(input_features, attention_mask=attention_mask, **kwargs)
-    from transformers.modeling_outputs import BaseModelOutput
 
+
+def _encoder_body(self, x: torch.Tensor) -> torch.Tensor:
+    """Front-end + every encoder layer: the residual stream BEFORE the final LayerNorm."""
     expected = self.config.max_source_positions * self.conv1.stride[0] * self.conv2.stride[0]
     if x.shape[-1] != expected:
         raise ValueError(f"Whisper expects the mel input features to be of length {expected}, but found {x.shape[-1]}. "
@@ -417,8 +415,26 @@ def _encoder_forward(self, input_features, attention_mask=None, **kwargs):
         h = F.gelu(self.conv2(F.gelu(self.conv1(x)))).permute(0, 2, 1) + self.embed_positions.weight
     for layer in self.layers:
         h = layer(h, None)
-    ln = pk["ln"].get()
-    h = ops.layernorm_fwd(h.contiguous(), ln.W, ln.b, self.layer_norm.eps)
+    return h.contiguous()
+
+
+def encoder_pre_ln(enc: nn.Module, input_features: torch.Tensor) -> Optional[torch.Tensor]:
+    """The fused encoder's residual stream before ``layer_norm`` (for consumers that fold that LayerNorm into their own
+    first pass: the LID router, lid_router.AdapterRouter), or None when the fused path does not apply."""
+    if not hasattr(enc, "_sar_pack") or not _encoder_fast_ok(enc, input_features, {}):
+        return None
+    return _encoder_body(enc, input_features)
+
+
+def _encoder_forward(self, input_features, attention_mask=None, **kwargs):
+    """WhisperEncoder.forward ($HF/models/whisper/modeling_whisper.py:590-647) without HF's per-call bookkeeping."""
+    if not _encoder_fast_ok(self, input_features, kwargs):
+        return self._sar_hf_forward(input_features, attention_mask=attention_mask, **kwargs)
+    from transformers.modeling_outputs import BaseModelOutput
+
+    h = _encoder_body(self, input_features)
+    ln = self._sar_pack["ln"].get()
+    h = ops.layernorm_fwd(h, ln.W, ln.b, self.layer_norm.eps)
     return BaseModelOutput(last_hidden_state=h)
 
 

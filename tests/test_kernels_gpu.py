@@ -184,6 +184,31 @@ def test_k2_ties_pick_first_index(cuda_dev):
     assert out.idx.cpu().tolist() == [1, 1, 1]                                   # torch.argmax tie rule
 
 
+@pytest.mark.parametrize("B,T,d,C", [(5, 1500, 768, 4), (3, 333, 1024, 4), (4, 257, 1280, 8), (6, 100, 256, 4)])
+def test_k2_with_the_encoder_final_layernorm_folded_in(cuda_dev, B, T, d, C):
+    """sar_router_fwd_fused_ln on the encoder's PRE-LayerNorm residual stream == LayerNorm kernel + K2 on its bf16 output
+    (SURVEY §8(f)-4): indices / perm / segments bit-exact, logits to fp32 summation noise; and both agree with the
+    reference head's restatement applied to bf16(LayerNorm(h))."""
+    g = torch.Generator().manual_seed(d + T)
+    sd = fixtures.make_router_state_dict(d, C)
+    feats, _ = fixtures.make_encoder_states(B, T, d, C, dtype=torch.float32)
+    h_pre = (feats * 2.5 + 0.7).to(torch.bfloat16)                    # un-normalised residual stream
+    gam = (1.0 + 0.1 * torch.randn(d, generator=g)).to(torch.bfloat16)
+    bet = (0.1 * torch.randn(d, generator=g)).to(torch.bfloat16)
+    dev = cuda_dev
+    params = ops.RouterParams.from_state_dict(sd, dev)
+    fused = ops.router_fwd(h_pre.to(dev), params, pre_ln=(gam.to(dev), bet.to(dev), 1e-5))
+    x = ops.layernorm_fwd(h_pre.to(dev), gam.to(dev), bet.to(dev), 1e-5)
+    two = ops.router_fwd(x, params)
+    assert torch.equal(fused.idx, two.idx) and torch.equal(fused.perm, two.perm)
+    assert torch.equal(fused.seg_starts, two.seg_starts)
+    assert (fused.logits - two.logits).abs().max().item() <= 2e-3     # x may differ from the fused path's by one bf16 ulp
+    ref = orouter.classifier_forward(x.cpu(), sd)
+    assert orouter.top2_margin(ref["logits"]).min() > 2e-2
+    assert torch.equal(fused.idx.cpu().long(), ref["probs"].argmax(-1))
+    assert (fused.logits.cpu() - ref["logits"]).abs().max() <= 2e-3
+
+
 # ------------------------------------------------------------------------------------------------ K3
 @pytest.mark.parametrize("B,T,d,r,n,bo", [(2, 128, 128, 16, 1, 0), (4, 300, 768, 16, 3, 3), (3, 1500, 768, 16, 1, 0),
                                           (3, 200, 1024, 32, 2, 0), (2, 130, 1280, 64, 2, 0), (2, 77, 768, 48, 2, 0)])

@@ -128,6 +128,21 @@ def test_forward_public_api_and_language_names(micro):
     assert rel_err(out["logits"], ref["logits"]) <= LOGIT_TOL
 
 
+def test_fused_lid_pass_equals_the_two_step_api(micro):
+    """AdapterRouter.route_inputs (encoder final LayerNorm + LID LayerNorm + mean-pool inside K2, on the residual stream)
+    gives what detect_indices(extract_encoder_features(x)) gives: same adapters, same probabilities."""
+    s = micro
+    x, *_ = s.batch(8, 4, "skewed", seed=6)
+    xg = x.to(s.dev).to(torch.bfloat16)
+    with torch.no_grad():
+        fused = s.router.route_inputs(xg)
+        two = s.router.detect_indices(s.router.extract_encoder_features(xg))
+    assert torch.equal(fused.idx, two.idx) and torch.equal(fused.perm, two.perm)
+    assert (fused.probs - two.probs).abs().max().item() <= 1e-3
+    ref_idx, _, _ = s.oracle.detect(x)
+    assert torch.equal(fused.idx.cpu().long(), ref_idx)
+
+
 def test_lid_features_come_from_base_weights(micro):
     """The LID pass must not see any adapter: features equal those of the un-adapted oracle encoder."""
     s = micro
@@ -512,7 +527,9 @@ def test_fused_blocks_are_what_the_micro_model_runs(micro):
         micro.router(x.to(micro.dev).to(torch.bfloat16), labels=labels.to(micro.dev))
     n_enc, n_dec = len(w.model.encoder.layers), len(w.model.decoder.layers)
     assert ops.LAUNCHES["k1"] == 0                                    # no module-slot K1 calls: the layer bodies are fused
-    assert ops.LAUNCHES["ln"] >= 2 * (2 * n_enc + 1) + 3 * n_dec + 1   # LID pass + routed pass
+    # LID pass: 2 per encoder layer (its final LayerNorm runs inside K2); routed pass: 2 per encoder layer + final,
+    # 3 per decoder layer + final
+    assert ops.LAUNCHES["ln"] >= 2 * 2 * n_enc + 1 + 3 * n_dec + 1
     assert ops.LAUNCHES["linear"] >= 2 * 3 * n_enc + 4 * n_dec
     assert ops.LAUNCHES["proj"] >= 2 * n_enc + 3 * n_dec
     assert ops.LAUNCHES["k2"] == 2
