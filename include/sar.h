@@ -121,6 +121,21 @@ int sar_attn_proj_fwd(const void* x, int x_head_major, const void* W_cat, const 
                       int d_out, int r, int n_adapters, float scale, uint32_t flags, void* ws, void* stream);
 
 /*
+ * sar_attn_proj_fwd with a per-utterance WEIGHTED MIX of adapters inside the low-rank term (an opt-in
+ * alternative to the reference's soft routing, src/models/adapter_router.py:627-670, which runs every adapter's whole
+ * model and mixes logits):   y = x·Wᵀ + b + Σ_g mix_w[b, g] · scale · (x·A_gᵀ)·B_gᵀ.
+ * The caller stacks the language adapters ALONG THE RANK into one merged adapter per set (A_cat [n_sets, r, d_in] with
+ * r = mix_groups * mix_group_rank <= 64, Bp_cat [n_sets, d_out, SAR_RPAD], n_adapters = 1, utt_adapter[b] = 0); the U
+ * pass scales rank columns [g*mix_group_rank, (g+1)*mix_group_rank) of utterance b by mix_w[b*mix_groups + g] before the
+ * single bf16 rounding.  Split path only (ws != NULL).  mix_w: fp32 [B, mix_groups] device pointer.
+ */
+int sar_attn_proj_fwd_mix(const void* x, int x_head_major, const void* W_cat, const void* bias_cat, const void* A_cat,
+                          const void* Bp_cat, const int32_t* utt_adapter, void* const* y, const int32_t* seg_set,
+                          const float* seg_scale, int n_seg, int n_sets, int y_head_major, int B, int T, int d_in,
+                          int d_out, int r, int n_adapters, float scale, uint32_t flags, void* ws, const float* mix_w,
+                          int mix_groups, int mix_group_rank, void* stream);
+
+/*
  * Row-indexed form of sar_attn_proj_fwd for decode steps (one token per utterance: rows of different adapters share
  * a tile).  The base projections of all segments run as ONE dense launch over the M rows; one gathered BGMV launch
  * adds seg_scale[s]·(scale·x_m·A_{set,k}ᵀ)·B_{set,k}ᵀ, k = row_adapter[m], to every LoRA'd segment.

@@ -129,10 +129,19 @@ class OracleLoRALinear(nn.Module):
         self.base = base
         self.A, self.B, self.scaling = A, B, scaling
         self.active = -1
+        self.mix: Optional[torch.Tensor] = None      # [n_adapters] weights of the current utterance (soft_fused)
         self.capture: Optional[list] = None
 
     def forward(self, x):
         k = self.active
+        if self.mix is not None:
+            # soft_fused (the product's opt-in strategy): y = base(x) + Σ_k w_k · s · B_k A_k x
+            y = olora.lora_linear(x, self.base.weight, self.base.bias, None, None, self.scaling)
+            for j in range(self.A.shape[0]):
+                y = y + float(self.mix[j]) * self.scaling * F.linear(F.linear(x, self.A[j].to(x.dtype)), self.B[j].to(x.dtype))
+            if self.capture is not None:
+                self.capture.append(y.detach())
+            return y
         y = olora.lora_linear(x, self.base.weight, self.base.bias, None if k < 0 else self.A[k].to(x.dtype),
                               None if k < 0 else self.B[k].to(x.dtype), self.scaling)
         if self.capture is not None:
@@ -224,6 +233,24 @@ class RoutedWhisperOracle:
                 l = probs[:, k].mean() * o.loss
                 loss = l if loss is None else loss + l
         return {"logits": weighted, "loss": loss, "probs": probs}
+
+    @torch.no_grad()
+    def forward_soft_fused(self, input_features: torch.Tensor, decoder_input_ids: torch.Tensor, weights: torch.Tensor,
+                           labels: Optional[torch.Tensor] = None):
+        """The product's opt-in ``soft_fused`` strategy (not a reference strategy): per utterance ONE forward whose every
+        LoRA'd projection applies Σ_k weights[b,k]·s·B_k A_k x; loss aggregated like hard routing."""
+        logits, losses = [], []
+        for i in range(input_features.shape[0]):
+            for m in self.mods.values():
+                m.mix = weights[i]
+            out = self.model(input_features=input_features[i:i + 1], decoder_input_ids=decoder_input_ids[i:i + 1])
+            logits.append(out.logits)
+            if labels is not None:
+                V = out.logits.shape[-1]
+                losses.append(F.cross_entropy(out.logits.reshape(-1, V), labels[i].reshape(-1), ignore_index=-100))
+        for m in self.mods.values():
+            m.mix = None
+        return {"logits": torch.cat(logits, 0), "loss": torch.stack(losses).mean() if losses else None}
 
     @torch.no_grad()
     def forward_threshold(self, input_features: torch.Tensor, threshold: float, labels: Optional[torch.Tensor] = None,

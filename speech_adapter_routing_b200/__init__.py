@@ -15,7 +15,7 @@ from .lora_linear import RoutedLoRALinear
 from .peft_compat import LoraConfig, PeftModel, get_peft_model, inject_lora, lora_modules
 from .whisper_adapters import WhisperLoRA, create_whisper_lora, load_whisper_lora_from_checkpoint
 from .lid_router import AdapterRouter, EncoderFeatureExtractor, LanguageClassifier
-from .routing import base_only, current_utt_adapter, refresh_operands, route, route_base
+from .routing import base_only, current_utt_adapter, refresh_operands, route, route_base, route_mix
 from .whisper_blocks import install_fused_blocks, uninstall_fused_blocks
 from .logmel import log_mel_spectrogram
 
@@ -24,5 +24,5 @@ __all__ = [
     "get_model_name", "get_model_info", "whisper_config", "MODEL_NAME_MAP", "LANGUAGE_CODES",
     "LanguageClassifier", "EncoderFeatureExtractor", "AdapterRouter", "RoutedLoRALinear", "LoraConfig", "PeftModel",
     "get_peft_model", "inject_lora", "lora_modules", "route", "route_base", "base_only", "current_utt_adapter",
-    "install_fused_blocks", "uninstall_fused_blocks", "log_mel_spectrogram", "refresh_operands",
+    "install_fused_blocks", "uninstall_fused_blocks", "log_mel_spectrogram", "refresh_operands", "route_mix",
 ]

@@ -30,6 +30,7 @@ _SIGNATURES = {
     "sar_workspace_bytes": (c_int64, [c_int, c_int64, c_int64, c_int64, c_int64, c_int64]),
     "sar_qv_lora_fwd": (c_int, [c_void_p] * 5 + [c_void_p, c_void_p, c_void_p] + [c_int] * 6 + [c_float, c_uint32, c_void_p]),
     "sar_attn_proj_fwd": (c_int, [c_void_p, c_int] + [c_void_p] * 8 + [c_int] * 9 + [c_float, c_uint32, c_void_p, c_void_p]),
+    "sar_attn_proj_fwd_mix": (c_int, [c_void_p, c_int] + [c_void_p] * 8 + [c_int] * 9 + [c_float, c_uint32, c_void_p, c_void_p, c_int, c_int, c_void_p]),
     "sar_attn_proj_fwd_rows": (c_int, [c_void_p] * 9 + [c_int] * 7 + [c_float, c_uint32, c_void_p]),
     "sar_qv_lora_fwd_pair": (c_int, [c_void_p] * 8 + [c_int] * 6 + [c_float, c_uint32, c_void_p]),
     "sar_linear_fwd": (c_int, [c_void_p, c_int] + [c_void_p] * 4 + [c_int] * 5 + [c_uint32, c_void_p]),

@@ -58,6 +58,10 @@ struct K1V2Params {
   __nv_bfloat16* u_out;
   int u_only;        // LORA kernels: compute and save U = scale·X·A_kᵀ only (no output tiles): the split path's first launch
   int u_ld;          // > 0: u_out is [n_sets][B, T, u_ld = r] (one compact plane per LoRA set); 0: legacy [B*T, r], set 0 only
+  // weighted multi-adapter mix (soft_fused routing): the "adapter" is the concatenation of n language adapters along the
+  // rank (A [n*r0, d], B [d_out, n*r0]); rank columns [g*r0, (g+1)*r0) of utterance b's U are scaled by u_w[b*u_w_ld + g]
+  const float* u_w;
+  int u_w_ld, u_w_group;
 };
 
 enum : int { EPI_RES = 1, EPI_GELU = 2, EPI_SCALE = 4 };
@@ -416,9 +420,10 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
             tmem_ld_32x16(tmem_base + lane_addr + u_col + 64 * s + j * 16, v);
             tmem_ld_wait();
             uint32_t pk[8];
+            const float sc = p.u_w ? p.scale * p.u_w[static_cast<size_t>(b) * p.u_w_ld + (j * 16) / p.u_w_group] : p.scale;
 #pragma unroll
             for (int i = 0; i < 8; ++i)
-              pk[i] = pack_bf16x2(__uint_as_float(v[2 * i]) * p.scale, __uint_as_float(v[2 * i + 1]) * p.scale);
+              pk[i] = pack_bf16x2(__uint_as_float(v[2 * i]) * sc, __uint_as_float(v[2 * i + 1]) * sc);
             if (!p.u_only) {   // the smem operand tile is only needed when this kernel also runs the output tiles
               st_shared_v4(u_row + (((2 * j) ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
               st_shared_v4(u_row + (((2 * j + 1) ^ sw) << 4), pk[4], pk[5], pk[6], pk[7]);
@@ -594,6 +599,9 @@ static int k1v2_launch(const K1Args& a, cudaStream_t stream) {
   }
   p.total_steps = static_cast<long long>(a.B) * p.tiles_per_utt * p.n_tiles;
   p.scale = a.scale;
+  p.u_w = has_lora ? a.u_w : nullptr;
+  p.u_w_ld = a.u_w_ld;
+  p.u_w_group = a.u_w_group > 0 ? a.u_w_group : 16;
   p.swap_halves = a.swap_halves;
   p.utt_adapter = has_lora ? a.utt_adapter : nullptr;
   p.bias = reinterpret_cast<const __nv_bfloat16*>(a.bias);

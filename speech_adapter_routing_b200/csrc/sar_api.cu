@@ -133,10 +133,11 @@ int sar_qv_lora_fwd(const void* x, const void* W, const void* bias, const void* 
   return k1_qv_lora_fwd(a, static_cast<cudaStream_t>(stream));
 }
 
-int sar_attn_proj_fwd(const void* x, int x_head_major, const void* W_cat, const void* bias_cat, const void* A_cat,
-                      const void* Bp_cat, const int32_t* utt_adapter, void* const* y, const int32_t* seg_set,
-                      const float* seg_scale, int n_seg, int n_sets, int y_head_major, int B, int T, int d_in,
-                      int d_out, int r, int n_adapters, float scale, uint32_t flags, void* ws, void* stream) {
+static int attn_proj_entry(const void* x, int x_head_major, const void* W_cat, const void* bias_cat, const void* A_cat,
+                           const void* Bp_cat, const int32_t* utt_adapter, void* const* y, const int32_t* seg_set,
+                           const float* seg_scale, int n_seg, int n_sets, int y_head_major, int B, int T, int d_in,
+                           int d_out, int r, int n_adapters, float scale, uint32_t flags, void* ws, const float* mix_w,
+                           int mix_groups, int mix_group_rank, void* stream) {
   int rc = require_sm100();
   if (rc) return rc;
   if (!y || !seg_set || !seg_scale || n_seg < 1 || n_seg > 3) return fail(SAR_EINVAL, "sar_attn_proj_fwd: bad segments");
@@ -148,6 +149,10 @@ int sar_attn_proj_fwd(const void* x, int x_head_major, const void* W_cat, const 
   a.grid_override = static_cast<int>((flags >> 18) & 0x3FF);
   a.n_seg = n_seg; a.n_sets = n_sets; a.x_head_major = x_head_major; a.y_head_major = y_head_major;
   a.u_ws = ws;
+  a.u_w = mix_w; a.u_w_ld = mix_groups; a.u_w_group = mix_group_rank;
+  if (mix_w && (mix_groups < 1 || mix_group_rank < 16 || mix_group_rank % 16 || mix_groups * mix_group_rank != r))
+    return fail(SAR_EINVAL, "sar_attn_proj_fwd_mix: r must equal mix_groups * mix_group_rank (a multiple of 16)");
+  if (mix_w && !ws) return fail(SAR_EINVAL, "sar_attn_proj_fwd_mix: needs the split path (ws)");
   a.u_phase = (flags & SAR_FLAG_U_ONLY) ? 1 : ((flags & SAR_FLAG_U_READY) ? 2 : 0);
   if (a.u_phase && !ws) return fail(SAR_EINVAL, "sar_attn_proj_fwd: U_ONLY / U_READY need the U workspace");
   for (int s = 0; s < n_seg; ++s) {
@@ -160,6 +165,25 @@ int sar_attn_proj_fwd(const void* x, int x_head_major, const void* W_cat, const 
     a.seg_scale[s] = 1.0f;
   }
   return attn_proj_fwd(a, static_cast<cudaStream_t>(stream));
+}
+
+int sar_attn_proj_fwd(const void* x, int x_head_major, const void* W_cat, const void* bias_cat, const void* A_cat,
+                      const void* Bp_cat, const int32_t* utt_adapter, void* const* y, const int32_t* seg_set,
+                      const float* seg_scale, int n_seg, int n_sets, int y_head_major, int B, int T, int d_in,
+                      int d_out, int r, int n_adapters, float scale, uint32_t flags, void* ws, void* stream) {
+  return attn_proj_entry(x, x_head_major, W_cat, bias_cat, A_cat, Bp_cat, utt_adapter, y, seg_set, seg_scale, n_seg, n_sets,
+                         y_head_major, B, T, d_in, d_out, r, n_adapters, scale, flags, ws, nullptr, 0, 0, stream);
+}
+
+int sar_attn_proj_fwd_mix(const void* x, int x_head_major, const void* W_cat, const void* bias_cat, const void* A_cat,
+                          const void* Bp_cat, const int32_t* utt_adapter, void* const* y, const int32_t* seg_set,
+                          const float* seg_scale, int n_seg, int n_sets, int y_head_major, int B, int T, int d_in,
+                          int d_out, int r, int n_adapters, float scale, uint32_t flags, void* ws, const float* mix_w,
+                          int mix_groups, int mix_group_rank, void* stream) {
+  if (!mix_w) return fail(SAR_EINVAL, "sar_attn_proj_fwd_mix: null mix_w");
+  return attn_proj_entry(x, x_head_major, W_cat, bias_cat, A_cat, Bp_cat, utt_adapter, y, seg_set, seg_scale, n_seg, n_sets,
+                         y_head_major, B, T, d_in, d_out, r, n_adapters, scale, flags, ws, mix_w, mix_groups, mix_group_rank,
+                         stream);
 }
 
 int sar_attn_proj_fwd_rows(const void* x, const void* W_cat, const void* bias_cat, const void* A_cat,

@@ -66,6 +66,8 @@ struct K1Args {
   int res_broadcast;                 // 1: the same [T, d_out] residual for every b (positional embedding)
   // ---- split LoRA path: U to a caller workspace, then the dense kernel with one extra K block per tile
   void* u_ws;        // bf16 [n_sets][B, T, r] workspace, or null = single-launch kernel (U stays in shared memory)
+  const float* u_w;  // fp32 [B, u_w_ld] per-utterance weights of the rank-column groups of U (null = none): soft_fused mix
+  int u_w_ld, u_w_group;   // groups per utterance / rank columns per group (the language adapters' own rank, % 16 == 0)
   int u_phase;       // split path: 0 = both launches, 1 = U pass only (y may be null), 2 = dense launch only (ws holds U)
   int u_only;        // internal: run only the U pass
   int u_ld;          // internal: > 0 = u_out is [n_sets][B, T, u_ld] with u_ld == r (one plane per LoRA set)

@@ -24,7 +24,7 @@ import torch.nn.functional as F
 from . import ops
 from .lora_linear import RoutedLoRALinear
 from .peft_compat import LoraConfig, PeftModel, inject_lora, lora_modules
-from .routing import base_only, operand_epoch, route, route_base
+from .routing import base_only, operand_epoch, route, route_base, route_mix
 
 logger = logging.getLogger(__name__)
 FUSED_LID = __import__("os").environ.get("SAR_FUSED_LID", "1") != "0"   # LID pass ends inside K2 (A/B switch)
@@ -437,6 +437,8 @@ class AdapterRouter(nn.Module):
             return self._soft_routing(input_features, routed.probs, labels, **kwargs)
         if self.strategy == "threshold":
             return self._threshold_routing(input_features, routed.probs, labels, **kwargs)
+        if self.strategy == "soft_fused":
+            return self._soft_fused_routing(input_features, routed.probs, labels, **kwargs)
         raise ValueError(f"Unknown routing strategy: {self.strategy}")
 
     def _hard_routing(self, input_features: torch.Tensor, predicted: Union[torch.Tensor, List[str]],
@@ -478,6 +480,31 @@ class AdapterRouter(nn.Module):
                 l = probs[:, i].mean() * out.loss
                 loss = l if loss is None else loss + l
         return {"loss": loss, "logits": weighted, "probs": probs}
+
+    def _soft_fused_routing(self, input_features: torch.Tensor, probs: torch.Tensor,
+                            labels: Optional[torch.Tensor] = None, top_k: Optional[int] = None,
+                            **kwargs) -> Dict[str, torch.Tensor]:
+        """Opt-in alternative to the reference's soft strategy (NOT the reference's semantics, which
+        mix the LOGITS of n full forwards, :627-670): ONE forward in which every LoRA'd projection applies the
+        probability-weighted mix of all adapters,  y = base(x) + Σ_k p[b,k] · s · B_k A_k x,  inside the fused kernels
+        (the adapters stacked along the rank, U scaled per utterance and adapter).  With one-hot ``probs`` it is exactly
+        hard routing; the loss uses hard routing's aggregation (mean over utterances of token-mean CE).  ``top_k``
+        keeps the k most probable adapters per utterance (renormalised)."""
+        w = probs.float()
+        if top_k is not None and top_k < w.shape[1]:
+            kth = w.topk(top_k, dim=-1).values[:, -1:]
+            w = torch.where(w >= kth, w, torch.zeros_like(w))
+            w = w / w.sum(dim=-1, keepdim=True)
+        kw = {k: v for k, v in kwargs.items() if k in ("attention_mask", "decoder_attention_mask")}
+        with route_mix(w):
+            out = self.whisper(input_features=input_features, labels=None, use_cache=False,
+                               decoder_input_ids=self._decoder_inputs(labels, kwargs), **kw)
+        result: Dict[str, torch.Tensor] = {}
+        if labels is not None:
+            result["loss"] = _per_utterance_loss(out.logits, labels)
+        result["logits"] = out.logits
+        result["probs"] = probs
+        return result
 
     def _threshold_routing(self, input_features: torch.Tensor, probs: torch.Tensor,
                            labels: Optional[torch.Tensor] = None, **kwargs) -> Dict[str, torch.Tensor]:

@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .routing import current_utt_adapter, operand_epoch, refresh_operands, routing_base_only
+from .routing import current_mix_weights, current_utt_adapter, operand_epoch, refresh_operands, routing_base_only
 
 
 class _QVLoRAFn(torch.autograd.Function):
@@ -215,6 +215,9 @@ class RoutedLoRALinear(nn.Module):
         if not x.is_cuda:
             raise RuntimeError("RoutedLoRALinear runs on libsar's sm_100a kernels only (no CPU fallback); "
                                "move the model and inputs to a B200")
+        if current_mix_weights() is not None:
+            raise NotImplementedError("soft_fused routing runs on the fused Whisper blocks only (bf16 CUDA inference with "
+                                      "head_dim 64); this projection was reached through HF's layer body")
         in_dtype = x.dtype
         lead = x.shape[:-1]
         if x.dim() == 2:

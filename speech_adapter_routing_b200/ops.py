@@ -124,7 +124,8 @@ def attn_proj_fwd(x: torch.Tensor, W_cat: torch.Tensor, bias_cat: Optional[torch
                   A_cat: Optional[torch.Tensor], Bp_cat: Optional[torch.Tensor], utt_adapter: Optional[torch.Tensor],
                   seg_set: Sequence[int], seg_scale: Sequence[float], n_sets: int, scale: float,
                   x_head_major: bool = False, y_head_major: bool = True, block_n: int = 0,
-                  grid: int = 0, split: Optional[bool] = None, u: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
+                  grid: int = 0, split: Optional[bool] = None, u: Optional[torch.Tensor] = None,
+                  mix_w: Optional[torch.Tensor] = None, mix_group_rank: int = 0) -> List[torch.Tensor]:
     """Fused attention projections (sar_attn_proj_fwd): up to three projections of the same x in one launch.
 
     x [B,T,d_in] (or [B,d_in/64,T,64] if ``x_head_major``); W_cat [n_seg*d_out, d_in]; A_cat [n_sets*n, r, d_in];
@@ -133,6 +134,8 @@ def attn_proj_fwd(x: torch.Tensor, W_cat: torch.Tensor, bias_cat: Optional[torch
     256-wide kernel with one extra K block; ``split=False``: the single-launch kernel that keeps U in shared memory;
     ``None`` (default): split from SPLIT_MIN_ROWS rows up (bit-identical results either way).
     ``u``: U already computed for this x ([n_sets, B, T, r], e.g. by ``layernorm_lora_u_fwd``): only the dense launch runs.
+    ``mix_w`` (fp32 [B, groups]) with ``mix_group_rank``: weighted mix of ``groups`` adapters stacked along the rank of ONE
+    merged adapter (sar_attn_proj_fwd_mix): rank columns of group g of utterance b are scaled by mix_w[b, g].
     """
     _need_cuda(x, W_cat, bias_cat, A_cat, Bp_cat, utt_adapter)
     x = _bf16c(x, "x"); W_cat = _bf16c(W_cat, "W_cat"); bias_cat = _bf16c(bias_cat, "bias_cat")
@@ -173,15 +176,25 @@ def attn_proj_fwd(x: torch.Tensor, W_cat: torch.Tensor, bias_cat: Optional[torch
             raise ValueError("u must be contiguous bf16 [n_sets, B, T, r]")
         ws = u
         flags |= _lib.SAR_FLAG_U_READY
-    elif has_lora and (split if split is not None else B * T >= SPLIT_MIN_ROWS):
+    elif has_lora and (mix_w is not None or (split if split is not None else B * T >= SPLIT_MIN_ROWS)):
         ws = torch.empty(n_sets * B * T * r, dtype=torch.bfloat16, device=x.device)   # U: [n_sets][B, T, r]
+    if mix_w is not None and has_lora:
+        if u is not None:
+            raise ValueError("mix_w and a precomputed u are mutually exclusive")
+        if mix_w.dtype != torch.float32 or not mix_w.is_contiguous() or mix_w.shape[0] != B or not mix_w.is_cuda:
+            raise ValueError("mix_w must be contiguous fp32 CUDA [B, groups]")
+        if mix_group_rank <= 0 or mix_w.shape[1] * mix_group_rank != r:
+            raise ValueError("mix_w.shape[1] * mix_group_rank must equal the merged rank r")
 
     def launch():
-        check(lib().sar_attn_proj_fwd(_ptr(x), int(x_head_major), _ptr(W_cat), _ptr(bias_cat),
-                                      _ptr(A_cat) if has_lora else None, _ptr(Bp_cat) if has_lora else None,
-                                      _ptr(utt_adapter) if has_lora else None, yp, ss, sc, n_seg,
-                                      n_sets if has_lora else 1, int(y_head_major), B, T, d_in, d_out, r, n_adapters,
-                                      float(scale), flags, _ptr(ws), _stream(x)))
+        common = (_ptr(x), int(x_head_major), _ptr(W_cat), _ptr(bias_cat), _ptr(A_cat) if has_lora else None,
+                  _ptr(Bp_cat) if has_lora else None, _ptr(utt_adapter) if has_lora else None, yp, ss, sc, n_seg,
+                  n_sets if has_lora else 1, int(y_head_major), B, T, d_in, d_out, r, n_adapters, float(scale), flags,
+                  _ptr(ws))
+        if mix_w is not None and has_lora:
+            check(lib().sar_attn_proj_fwd_mix(*common, _ptr(mix_w), int(mix_w.shape[1]), int(mix_group_rank), _stream(x)))
+        else:
+            check(lib().sar_attn_proj_fwd(*common, _stream(x)))
     n_lora = sum(1 for s in seg_set if s >= 0) if has_lora else 0
     # algorithmic flops of THIS call: with U precomputed (fused into the LayerNorm kernel) the down-projection
     # 2·M·r·d_in per set is not done here and is not credited to this kernel

@@ -20,6 +20,7 @@ class _RoutingState(threading.local):
         self.utt_adapter: Optional[torch.Tensor] = None
         self.active = False
         self.base_only = False
+        self.mix_weights: Optional[torch.Tensor] = None
 
 
 _state = _RoutingState()
@@ -42,12 +43,31 @@ def routing_base_only() -> bool:
 
 @contextmanager
 def route_base():
-    prev = (_state.utt_adapter, _state.active, _state.base_only)
-    _state.utt_adapter, _state.active, _state.base_only = None, False, True
+    prev = (_state.utt_adapter, _state.active, _state.base_only, _state.mix_weights)
+    _state.utt_adapter, _state.active, _state.base_only, _state.mix_weights = None, False, True, None
     try:
         yield
     finally:
-        _state.utt_adapter, _state.active, _state.base_only = prev
+        _state.utt_adapter, _state.active, _state.base_only, _state.mix_weights = prev
+
+
+def current_mix_weights() -> Optional[torch.Tensor]:
+    """fp32 [B, n_adapters] device tensor set by ``route_mix(...)`` (soft_fused routing), or None."""
+    return _state.mix_weights
+
+
+@contextmanager
+def route_mix(weights: torch.Tensor):
+    """Run the enclosed forward with a per-utterance WEIGHTED MIX of all stacked adapters inside every LoRA'd projection:
+    y = base(x) + Σ_k weights[b, k] · s · B_k A_k x (lid_router.AdapterRouter strategy "soft_fused")."""
+    w = weights.detach().to(torch.float32).contiguous()
+    prev = (_state.utt_adapter, _state.active, _state.base_only, _state.mix_weights)
+    _state.utt_adapter = torch.zeros(w.shape[0], dtype=torch.int32, device=w.device)   # the one merged adapter
+    _state.active, _state.base_only, _state.mix_weights = True, False, w
+    try:
+        yield
+    finally:
+        _state.utt_adapter, _state.active, _state.base_only, _state.mix_weights = prev
 
 
 @contextmanager
@@ -58,12 +78,12 @@ def route(utt_adapter: Optional[torch.Tensor]):
         if utt_adapter.dtype != torch.int32:
             utt_adapter = utt_adapter.to(torch.int32)
         utt_adapter = utt_adapter.contiguous()
-    prev = (_state.utt_adapter, _state.active, _state.base_only)
-    _state.utt_adapter, _state.active, _state.base_only = utt_adapter, utt_adapter is not None, False
+    prev = (_state.utt_adapter, _state.active, _state.base_only, _state.mix_weights)
+    _state.utt_adapter, _state.active, _state.base_only, _state.mix_weights = utt_adapter, utt_adapter is not None, False, None
     try:
         yield
     finally:
-        _state.utt_adapter, _state.active, _state.base_only = prev
+        _state.utt_adapter, _state.active, _state.base_only, _state.mix_weights = prev
 
 
 def base_only(batch_size: int, device) -> torch.Tensor:

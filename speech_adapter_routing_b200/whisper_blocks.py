@@ -32,7 +32,7 @@ import torch.nn.functional as F
 from . import ops
 from ._lib import SAR_ACT_GELU, SAR_ACT_NONE
 from .lora_linear import RoutedLoRALinear
-from .routing import operand_epoch
+from .routing import current_mix_weights, operand_epoch
 
 FUSED_BLOCKS_ENABLED = True   # debug switch: False restores HF's layer bodies everywhere
 FUSED_LN_U = os.environ.get("SAR_FUSED_LN_U", "1") != "0"   # LayerNorm + LoRA down-projection in one pass (A/B switch)
@@ -118,10 +118,38 @@ class _ProjPack:
     def resolve_index(self, B: int, device) -> Optional[torch.Tensor]:
         return self.lora_mods[0].resolve_index(B, device) if self.lora_mods else None
 
+    @torch.no_grad()
+    def merged(self):
+        """The language adapters of every LoRA'd segment stacked ALONG THE RANK into one merged adapter per set —
+        A [n_sets, n*r, d_in], Bp [n_sets, d_out, 64] — for the weighted in-kernel mix (soft_fused routing).  None when
+        n*r exceeds the kernels' rank limit (64)."""
+        self.get()
+        if self.A is None:
+            return None
+        if getattr(self, "_merged_key", None) != self.key:
+            self._merged_key = self.key
+            self._merged = None
+            As, Bps = [], []
+            fold = [s != 1.0 and math.frexp(s)[0] == 0.5 for s in self.seg_scale]
+            for m, sc, f in zip(self.mods, self.seg_scale, fold):
+                if not (isinstance(m, RoutedLoRALinear) and m.adapter_order):
+                    continue
+                st = m._stacks()
+                n, rp, d_in = st["A"].shape
+                if n * rp > ops.SAR_RPAD:
+                    return None
+                As.append(st["A"].reshape(1, n * rp, d_in))
+                Bm = st["_Bm"].permute(1, 0, 2).reshape(m.out_features, n * rp)        # [d_out, n*r]: group g = adapter g
+                Bps.append(ops.pack_lora_b((Bm * sc if f else Bm).unsqueeze(0)))
+            self._merged = (torch.cat(As, 0).contiguous(), torch.cat(Bps, 0).contiguous(), rp)
+        return self._merged
+
     def fused_ln_u_ok(self, B: int, T: int, d: int, idx: Optional[torch.Tensor]) -> bool:
         """True when the LayerNorm feeding this call may also produce U = scale·x·A_kᵀ (ops.layernorm_lora_u_fwd): the
         split LoRA path would be taken and the fused kernel covers this (d, r, n_sets)."""
         if not FUSED_LN_U or idx is None or self.A is None or (T == 1 and B > 1) or B * T < ops.SPLIT_MIN_ROWS:
+            return False
+        if current_mix_weights() is not None:      # the weighted mix scales U per utterance inside the U pass
             return False
         key = (d, self.A.shape[1], self.n_sets)
         if getattr(self, "_lnu_key", None) != key:
@@ -131,6 +159,21 @@ class _ProjPack:
     def __call__(self, x: torch.Tensor, idx: Optional[torch.Tensor], u: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
         lora = idx is not None and self.A is not None
         B, T, d = x.shape
+        mix = current_mix_weights() if lora else None
+        if mix is not None:
+            mg = self.merged()
+            if mg is None:
+                raise NotImplementedError("soft_fused routing needs n_adapters * rank <= 64 (merged rank limit of the kernels)")
+            if mix.shape[0] != B:
+                raise ValueError(f"mix weights hold {mix.shape[0]} utterances but the batch has {B}")
+            A_m, Bp_m, rp = mg
+            zeros = torch.zeros(B, dtype=torch.int32, device=x.device)
+            ys = ops.attn_proj_fwd(x, self.W, self.bias, A_m, Bp_m, zeros, self.seg_set, self.kernel_scale, self.n_sets,
+                                   self.scale, y_head_major=True, mix_w=mix, mix_group_rank=rp)
+            if PROJ_CAPTURE is not None:
+                for m, y, s in zip(self.mods, ys, self.seg_scale):
+                    PROJ_CAPTURE.setdefault(id(m), []).append((y.transpose(1, 2).reshape(B, T, -1).float() / s).detach())
+            return ys
         if T == 1 and B > 1:
             # decode step: one token per utterance — rows of different adapters share a tile (base GEMM over the B
             # rows + gathered BGMV); [B, d_out] is bit-for-bit the head-major [B, h, 1, 64] layout

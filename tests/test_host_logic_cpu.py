@@ -369,3 +369,36 @@ def test_adapter_router_rejects_a_classifier_with_the_wrong_class_count(micro_mo
         sar.AdapterRouter.from_stacked(m, clf, langs)
     ok = sar.LanguageClassifier(input_dim=m.config.d_model, num_classes=2, languages=langs)
     assert sar.AdapterRouter.from_stacked(m, ok, langs).languages == langs
+
+
+def test_route_mix_context_and_merged_adapter_layout(micro_model):
+    """soft_fused plumbing on the host: the routing context carries fp32 weights and one merged adapter index; the
+    merged stacks put adapter g's rank rows / columns at [g*r, (g+1)*r)."""
+    import copy
+    from speech_adapter_routing_b200 import whisper_blocks as wb
+
+    w = torch.tensor([[0.25, 0.75], [1.0, 0.0]])
+    with sar.route_mix(w):
+        assert torch.equal(routing.current_mix_weights(), w) and routing.current_utt_adapter().tolist() == [0, 0]
+        with sar.route_base():
+            assert routing.current_mix_weights() is None
+        assert routing.current_mix_weights() is not None
+    assert routing.current_mix_weights() is None and routing.current_utt_adapter() is None
+
+    m = copy.deepcopy(micro_model)
+    for name in ("a", "b"):
+        sar.inject_lora(m, sar.LoraConfig(r=16, lora_alpha=32, target_modules=["q_proj", "v_proj"]), adapter_name=name)
+    attn = m.model.encoder.layers[0].self_attn
+    with torch.no_grad():
+        for mod in (attn.q_proj, attn.v_proj):
+            for name in ("a", "b"):
+                mod.lora_B[name].weight.normal_(0, 0.02)
+    pack = wb._ProjPack([attn.q_proj, attn.k_proj, attn.v_proj], [0.125, 1.0, 1.0])
+    A_m, Bp_m, rp = pack.merged()
+    assert rp == 16 and tuple(A_m.shape) == (2, 32, 256) and tuple(Bp_m.shape) == (2, 256, 64)
+    assert torch.equal(A_m[0, 16:32].float(), attn.q_proj.lora_A["b"].weight.to(torch.bfloat16).float())
+    assert torch.equal(A_m[1, :16].float(), attn.v_proj.lora_A["a"].weight.to(torch.bfloat16).float())
+    # q's segment scale 2^-3 is folded into its B (exact), v's is 1
+    assert torch.equal(Bp_m[0, :, 16:32].float(), (attn.q_proj.lora_B["b"].weight * 0.125).to(torch.bfloat16).float())
+    assert torch.equal(Bp_m[1, :, :16].float(), attn.v_proj.lora_B["a"].weight.to(torch.bfloat16).float())
+    assert torch.count_nonzero(Bp_m[:, :, 32:]) == 0                       # rank padding

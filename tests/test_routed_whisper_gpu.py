@@ -215,6 +215,49 @@ def oracle_margins(s, x, want, idx):
     return m, absmax
 
 
+def test_soft_fused_strategy_weighted_mix_inside_the_projections(micro):
+    """strategy="soft_fused" (opt-in): ONE forward whose every LoRA'd projection applies
+    Σ_k p[b,k]·s·B_k A_k x inside the fused kernels — against its own oracle (per-utterance fp32 forward with the mixed
+    LoRA term), module by module and at the logits; one-hot weights reduce to hard routing; top_k renormalises."""
+    s = micro
+    x, dec, labels, _ = s.batch(6, 8, seed=14)
+    xg = x.to(s.dev).to(torch.bfloat16)
+    g = torch.Generator().manual_seed(3)
+    w = torch.softmax(torch.randn(6, s.C, generator=g) * 1.5, dim=-1)              # genuinely mixed weights
+    ref = s.oracle.forward_soft_fused(x, dec, w, labels)
+    for m in s.oracle.mods.values():
+        m.capture = None
+    with torch.no_grad():
+        with capture_lora_modules(s.router.whisper) as captured:
+            out = s.router._soft_fused_routing(xg, w.to(s.dev), labels.to(s.dev))
+    assert set(out) == {"loss", "logits", "probs"}
+    assert rel_err(out["logits"], ref["logits"]) <= LOGIT_TOL
+    assert abs(out["loss"].item() - ref["loss"].item()) <= 2e-2 * abs(ref["loss"].item())
+    assert len(captured) == len(s.oracle.mods)                                     # every q_proj / v_proj ran fused
+    # the public strategy switch: LID probabilities as weights
+    s.router.strategy = "soft_fused"
+    try:
+        with torch.no_grad():
+            pub = s.router(xg, labels=labels.to(s.dev))
+            probs = s.router.route_inputs(xg).probs
+    finally:
+        s.router.strategy = "hard"
+    want = s.oracle.forward_soft_fused(x, dec, probs.cpu(), labels)
+    assert rel_err(pub["logits"], want["logits"]) <= LOGIT_TOL
+    # one-hot weights == hard routing (same adapters, U from a different kernel: equal to bf16 rounding noise)
+    idx = torch.tensor([1, 3, 0, 2, 2, 1])
+    onehot = torch.nn.functional.one_hot(idx, s.C).float()
+    with torch.no_grad():
+        a = s.router._soft_fused_routing(xg, onehot.to(s.dev), labels.to(s.dev))
+        b = s.router._hard_routing(xg, idx.to(torch.int32).to(s.dev), labels.to(s.dev))
+    assert rel_err(a["logits"], b["logits"]) <= 1e-2 and abs(a["loss"].item() - b["loss"].item()) <= 1e-2
+    # top-1 of the mixed weights is hard routing on their argmax
+    with torch.no_grad():
+        t1 = s.router._soft_fused_routing(xg, w.to(s.dev), labels.to(s.dev), top_k=1)
+        h1 = s.router._hard_routing(xg, w.argmax(-1).to(torch.int32).to(s.dev), labels.to(s.dev))
+    assert rel_err(t1["logits"], h1["logits"]) <= 1e-2
+
+
 def test_greedy_generation_matches_oracle_tokens(micro):
     s = micro
     B, steps = 8, 32
