@@ -23,10 +23,14 @@
 // 128x64 tile against 2 x 128 clk of MMA), and with one thread per row (2 warps per SMSP) the ~250 non-MUFU
 // instructions of a tile issue at the 4-6 clk dependent-issue latency and leave the MUFU pipe half idle (measured: XU
 // 50 %, issue slots 48 %); four warps per SMSP interleave them.
+#include <cstdlib>
+
 #include "sar_internal.h"
 #include "sar_ptx.cuh"
 
 namespace sar {
+
+int attn_fwd2(const void* q, const void* k, const void* v, void* out, int BH, int Tq, int Tk, cudaStream_t stream);
 
 constexpr int FA_SOFTMAX_WARPS = 8;
 constexpr int FA_THREADS = (FA_SOFTMAX_WARPS + 3) * 32;   // + TMA producer, S issuer, PV issuer
@@ -301,6 +305,13 @@ int attn_fwd(const void* q, const void* k, const void* v, void* out, int BH, int
        reinterpret_cast<uintptr_t>(out)) & 15)
     return fail(SAR_EINVAL, "attn_fwd: pointers must be 16-byte aligned");
   if (causal && Tq != Tk) return fail(SAR_EINVAL, "attn_fwd: the causal mask is defined for Tq == Tk");
+  // long non-causal sequences (the encoder, long cross-attention): two query tiles per CTA, one thread per row
+  // (attn_fwd2.cu); SAR_ATTN_V2=0 keeps this kernel for A/B measurements
+  static const bool v2_on = [] {
+    const char* e = getenv("SAR_ATTN_V2");
+    return !(e && e[0] == '0');
+  }();
+  if (v2_on && !causal && Tq >= 384) return attn_fwd2(q, k, v, out, BH, Tq, Tk, stream);
   const DeviceInfo& dev = device_info();
   CUtensorMap tm_q, tm_k, tm_v;
   int rc;

@@ -385,6 +385,10 @@ def test_skinny_dense_matches_oracle(cuda_dev, M, d_in, d_out, gelu, res):
 @pytest.mark.parametrize("B,H,Tq,Tk,causal", [
     (1, 1, 128, 64, False), (2, 3, 200, 300, False), (1, 2, 1500, 1500, False), (2, 12, 128, 1500, False),
     (2, 3, 128, 128, True), (2, 2, 37, 37, True), (1, 2, 300, 300, True), (3, 2, 1, 77, False), (1, 20, 448, 448, True),
+    # long non-causal: the two-query-tile kernel (attn_fwd2.cu): ragged last key tile, second query tile partly / fully
+    # past Tq, cross-attention with Tq != Tk
+    (2, 3, 384, 1500, False), (1, 2, 448, 1500, False), (1, 3, 513, 200, False), (1, 2, 1024, 64, False),
+    (1, 1, 640, 1, False),
 ])
 def test_attn_fwd_matches_fp32_softmax(cuda_dev, B, H, Tq, Tk, causal):
     """sar_attn_fwd (tcgen05 flash-attention forward, head dim 64) vs fp32 softmax(q kᵀ) v on the same bf16 inputs:
