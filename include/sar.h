@@ -277,6 +277,30 @@ int sar_layernorm_lora_u_fwd(const void* h, const void* gamma, const void* beta,
 int sar_layernorm_lora_u_supported(int d, int r, int n_sets);
 
 /*
+ * Operand refresh for captured training steps.  PEFT reads lora_A / lora_B straight from the parameters on every
+ * forward (peft/tuners/lora/layer.py Linear.forward, called from src/models/whisper_lora.py:88-98), so an optimizer
+ * step is visible to the next forward by construction.  libsar's kernels read derived bf16 operands (rank-padded A
+ * stacks, 64-column B stacks, their transposes for sar_qv_lora_bwd, the concatenations of sar_attn_proj_fwd); when the
+ * training step is replayed as a CUDA graph no host code runs between optimizer steps, so this launch — a node of
+ * that graph — re-derives every operand block from the live fp32 (or bf16) parameters:
+ *   for each descriptor:  dst[i*dst_rs + j*dst_cs] = bf16(scale * src[i*src_rs + j*src_cs]),  i < rows, j < cols
+ * `desc` is a DEVICE array of n_desc descriptors (strides in elements); max_elems = max over descriptors of rows*cols.
+ * Padding rows / columns of the destination stacks are not touched (they stay zero).
+ */
+#define SAR_DTYPE_F32 0
+#define SAR_DTYPE_BF16 1
+typedef struct sar_refresh_desc {
+  const void* src; /* parameter block (device) */
+  void* dst;       /* bf16 operand block (device) */
+  int32_t rows, cols;
+  int64_t src_rs, src_cs; /* element strides of src along i, j */
+  int64_t dst_rs, dst_cs; /* element strides of dst along i, j */
+  float scale;
+  int32_t src_dtype; /* SAR_DTYPE_F32 | SAR_DTYPE_BF16 */
+} sar_refresh_desc;
+int sar_operand_refresh(const sar_refresh_desc* desc, int n_desc, int max_elems, void* stream);
+
+/*
  * Row-indexed variant for decode steps (T = 1 per utterance, rows of different adapters share a tile):
  *   y[m,:] = x[m,:]·Wᵀ + bias + scale·(x[m,:]·A_kᵀ)·B_kᵀ, k = row_adapter[m].
  * Replaces the per-sample adapter.generate loop of src/models/adapter_router.py:744-750 for the

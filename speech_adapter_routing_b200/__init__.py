@@ -18,11 +18,13 @@ from .lid_router import AdapterRouter, EncoderFeatureExtractor, LanguageClassifi
 from .routing import base_only, current_utt_adapter, refresh_operands, route, route_base, route_mix
 from .whisper_blocks import install_fused_blocks, uninstall_fused_blocks
 from .logmel import log_mel_spectrogram
+from .train_graph import GraphedTrainStep
+from .dist import FlatGradBucket
 
 __all__ = [
     "WhisperLoRA", "create_whisper_lora", "load_whisper_lora_from_checkpoint", "load_base_model", "get_processor",
     "get_model_name", "get_model_info", "whisper_config", "MODEL_NAME_MAP", "LANGUAGE_CODES",
     "LanguageClassifier", "EncoderFeatureExtractor", "AdapterRouter", "RoutedLoRALinear", "LoraConfig", "PeftModel",
     "get_peft_model", "inject_lora", "lora_modules", "route", "route_base", "base_only", "current_utt_adapter",
-    "install_fused_blocks", "uninstall_fused_blocks", "log_mel_spectrogram", "refresh_operands", "route_mix",
+    "install_fused_blocks", "uninstall_fused_blocks", "log_mel_spectrogram", "refresh_operands", "route_mix", "GraphedTrainStep", "FlatGradBucket",
 ]

@@ -21,6 +21,7 @@ SAR_FLAG_U_READY, SAR_FLAG_U_ONLY = 4, 8
 SAR_OP_QV_LORA_FWD, SAR_OP_ROUTER_FWD, SAR_OP_QV_LORA_BWD, SAR_OP_QV_LORA_FWD_ROWS, SAR_OP_ATTN_PROJ_FWD = 0, 1, 2, 3, 4
 SAR_RPAD = 64
 SAR_ACT_NONE, SAR_ACT_GELU = 0, 1
+SAR_DTYPE_F32, SAR_DTYPE_BF16 = 0, 1
 
 # name -> (restype, argtypes); mirrors include/sar.h one to one
 _SIGNATURES = {
@@ -43,6 +44,7 @@ _SIGNATURES = {
     "sar_layernorm_fwd": (c_int, [c_void_p] * 4 + [c_int64, c_int, c_float, c_void_p]),
     "sar_layernorm_lora_u_fwd": (c_int, [c_void_p] * 7 + [c_int] * 6 + [c_float, c_float, c_void_p]),
     "sar_layernorm_lora_u_supported": (c_int, [c_int] * 3),
+    "sar_operand_refresh": (c_int, [c_void_p, c_int, c_int, c_void_p]),
     "sar_qv_lora_fwd_rows": (c_int, [c_void_p] * 5 + [c_void_p, c_void_p] + [c_int] * 5 + [c_float, c_void_p, c_void_p]),
     "sar_router_fwd": (c_int, [c_void_p, c_int] + [c_void_p] * 12 + [c_int] * 6 + [c_void_p] * 5 + [c_void_p, c_void_p]),
     "sar_router_fwd_fused_ln": (c_int, [c_void_p, c_void_p, c_void_p, c_float] + [c_void_p] * 12 + [c_int] * 6 + [c_void_p] * 5 + [c_void_p, c_void_p]),

@@ -310,6 +310,12 @@ int sar_layernorm_lora_u_fwd(const void* h, const void* gamma, const void* beta,
 
 int sar_layernorm_lora_u_supported(int d, int r, int n_sets) { return ln_lora_u_supported(d, r, n_sets) ? 1 : 0; }
 
+int sar_operand_refresh(const sar_refresh_desc* desc, int n_desc, int max_elems, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  return operand_refresh(desc, n_desc, max_elems, static_cast<cudaStream_t>(stream));
+}
+
 int sar_qv_lora_fwd_rows(const void* x, const void* W, const void* bias, const void* A_stack, const void* Bp_stack,
                          const int32_t* row_adapter, void* y, int M, int d_in, int d_out, int r, int n_adapters,
                          float scale, void* ws, void* stream) {

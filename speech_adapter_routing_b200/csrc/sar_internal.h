@@ -93,6 +93,7 @@ int ln_lora_u_fwd(const void* h, const void* gamma, const void* beta, void* x, c
                   const int32_t* utt_adapter, void* u_out, int B, int T, int d, int r, int n_sets, int n_adapters,
                   float scale, float eps, cudaStream_t stream);
 bool ln_lora_u_supported(int d, int r, int n_sets);
+int operand_refresh(const void* desc, int n_desc, int max_elems, cudaStream_t stream);
 
 struct K2Args {
   const void* h;

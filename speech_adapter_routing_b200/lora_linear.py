@@ -180,8 +180,24 @@ class RoutedLoRALinear(nn.Module):
         if backward and "Wt" not in c:
             c["Wt"] = c["W"].t().contiguous()
             c["At"] = ops.pack_lora_b(c["A"].transpose(1, 2).contiguous())      # [n, d_in, 64]
-            c["Bt"] = c["_Bm"].to(torch.bfloat16).transpose(1, 2).contiguous()   # [n, r, d_out]
+            c["Bt"] = self._bm().to(torch.bfloat16).transpose(1, 2).contiguous()   # [n, r, d_out]
         return c
+
+    @torch.no_grad()
+    def _bm(self) -> torch.Tensor:
+        """fp32 [n, d_out, rp] stack of scaling-folded lora_B (source of Bt and of the merged soft_fused operands).  An
+        in-place operand refresh (operand_refresh.py) drops it; it is rebuilt from the parameters on demand."""
+        c = self._cache
+        if c.get("_Bm") is None:
+            names = self.adapter_order
+            rp = c["A"].shape[1]
+            scal = [self.scaling[n] for n in names]
+            uniform = all(abs(s - scal[0]) < 1e-12 for s in scal)
+            Bm = torch.zeros(len(names), self.out_features, rp, dtype=torch.float32, device=c["A"].device)
+            for k, n in enumerate(names):
+                Bm[k, :, : self.r[n]] = self.lora_B[n].weight.detach().float() * (1.0 if uniform else scal[k])
+            c["_Bm"] = Bm
+        return c["_Bm"]
 
     def _default_index(self, B: int, device) -> Optional[torch.Tensor]:
         if self.disable_adapters or self.active_adapter is None or not self.adapter_order:

@@ -14,7 +14,7 @@ from ._lib import SAR_FLAG_SAVE_U, SAR_RPAD, check, lib
 
 
 # ---- instrumentation used by bench.py: kernel-launch counts and (optional) per-launch CUDA-event timing ----------
-LAUNCHES = {"k1": 0, "k2": 0, "k3": 0, "rows": 0, "proj": 0, "linear": 0, "ln": 0, "attn": 0, "logmel": 0}   # kernels launched by libsar, by op (k2 = 2, k3 = 3, rows = 2)
+LAUNCHES = {"k1": 0, "k2": 0, "k3": 0, "rows": 0, "proj": 0, "linear": 0, "ln": 0, "attn": 0, "logmel": 0, "refresh": 0}   # kernels launched by libsar, by op (k2 = 2, k3 = 3, rows = 2)
 SPLIT_MIN_ROWS = int(__import__("os").environ.get("SAR_SPLIT_MIN_ROWS", "4096"))   # fewer rows: single-launch LoRA kernel (M = 8192, 768 -> 2304: split 79 us, single launch 91 us)
 K1_TIMELINE = None   # set to a list to record (B*T, d_in, d_out, r, has_lora, start_event, end_event) per K1 call
 

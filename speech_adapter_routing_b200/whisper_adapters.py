@@ -83,8 +83,33 @@ class WhisperLoRA(nn.Module):
                 attention_mask: Optional[torch.Tensor] = None, decoder_input_ids: Optional[torch.Tensor] = None,
                 decoder_attention_mask: Optional[torch.Tensor] = None, **kwargs) -> Dict[str, torch.Tensor]:
         # only the five supported arguments are forwarded; other kwargs are swallowed like the reference (:136-143)
+        extra = {}
+        if self.training and torch.is_grad_enabled() and labels is not None:
+            self._sync_lora_operands(input_features)
+            # teacher-forced training never reads the KV cache HF would build alongside the loss (HF itself switches
+            # it off under gradient checkpointing); without it the decoder layers take the fused forward+backward bodies
+            extra["use_cache"] = False
         return self.model(input_features=input_features, labels=labels, attention_mask=attention_mask,
-                          decoder_input_ids=decoder_input_ids, decoder_attention_mask=decoder_attention_mask)
+                          decoder_input_ids=decoder_input_ids, decoder_attention_mask=decoder_attention_mask, **extra)
+
+    def _sync_lora_operands(self, input_features: torch.Tensor) -> None:
+        """Training loop (src/training/trainer.py:251-268): after ``optimizer.step()`` the kernels' cached bf16 LoRA
+        operands are stale.  From the third step on they are re-derived by ONE launch (operand_refresh.py) instead of the
+        per-module host-side rebuild (~25 small kernels for each of the 72 LoRA'd projections and 48 fused calls)."""
+        if not input_features.is_cuda:
+            return
+        d = self.__dict__
+        r = d.get("_sar_refresh")
+        if r is not None:
+            if r.maybe_refresh():
+                return
+            d["_sar_refresh"] = None
+        steps = d.get("_sar_train_steps", 0)
+        d["_sar_train_steps"] = steps + 1
+        if steps >= 1:                      # the first step built every cache this object indexes
+            from .operand_refresh import OperandRefresh
+
+            d["_sar_refresh"] = OperandRefresh(self.model)
 
     def generate(self, input_features: torch.Tensor, max_new_tokens: int = 256, num_beams: int = 1,
                  language: Optional[str] = None, task: Optional[str] = None, **kwargs) -> torch.Tensor:

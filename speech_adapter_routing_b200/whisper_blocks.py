@@ -66,9 +66,12 @@ class _ProjPack:
         self.seg_scale = seg_scale
         self.key = None
 
+    def _current_key(self) -> Tuple:
+        return tuple(_pver(*_lin_params(m)) + _lora_key(m) for m in self.mods)
+
     @torch.no_grad()
     def get(self):
-        key = tuple(_pver(*_lin_params(m)) + _lora_key(m) for m in self.mods)
+        key = self._current_key()
         if key == self.key:
             return self
         self.key = key
@@ -139,7 +142,7 @@ class _ProjPack:
                 if n * rp > ops.SAR_RPAD:
                     return None
                 As.append(st["A"].reshape(1, n * rp, d_in))
-                Bm = st["_Bm"].permute(1, 0, 2).reshape(m.out_features, n * rp)        # [d_out, n*r]: group g = adapter g
+                Bm = m._bm().permute(1, 0, 2).reshape(m.out_features, n * rp)        # [d_out, n*r]: group g = adapter g
                 Bps.append(ops.pack_lora_b((Bm * sc if f else Bm).unsqueeze(0)))
             self._merged = (torch.cat(As, 0).contiguous(), torch.cat(Bps, 0).contiguous(), rp)
         return self._merged
@@ -309,6 +312,12 @@ def _sdpa(q, k, v, mask=None, causal=False):
 # ------------------------------------------------------------------------------------------------ layer bodies
 def _encoder_layer_forward(self, hidden_states: torch.Tensor, attention_mask: Optional[torch.Tensor] = None, **kwargs):
     pk = self._sar_pack
+    if attention_mask is None and torch.is_grad_enabled():
+        from . import whisper_train            # training: fused forward + backward of the whole layer (whisper_train.py)
+
+        out = whisper_train.encoder_layer_train(self, hidden_states, kwargs)
+        if out is not None:
+            return out
     if attention_mask is not None or not _fast_path_ok(self, hidden_states, kwargs):
         return self._sar_hf_forward(hidden_states, attention_mask, **kwargs)
     qkv = pk["self"].qkv.get()
@@ -330,6 +339,19 @@ def _decoder_layer_forward(self, hidden_states: torch.Tensor, attention_mask: Op
                            encoder_attention_mask: Optional[torch.Tensor] = None, past_key_values=None,
                            use_cache: Optional[bool] = True, **kwargs):
     pk = self._sar_pack
+    if torch.is_grad_enabled():
+        from . import whisper_train
+
+        causal_only = attention_mask is None or (
+            whisper_train.ASSUME_CAUSAL_MASK and attention_mask.dim() == 4 and attention_mask.shape[1] == 1
+            and attention_mask.shape[-1] == attention_mask.shape[-2] == hidden_states.shape[1])
+        if past_key_values is None and causal_only and encoder_attention_mask is None:
+            out = whisper_train.decoder_layer_train(self, hidden_states, encoder_hidden_states, kwargs)
+            if out is not None:
+                return out
+        else:
+            whisper_train.REFUSED["decoder"] = (f"cache {type(past_key_values).__name__} / mask "
+                                                f"{None if attention_mask is None else tuple(attention_mask.shape)}")
     fast = (past_key_values is None and encoder_attention_mask is None and _fast_path_ok(self, hidden_states, kwargs)
             and (encoder_hidden_states is None or
                  (encoder_hidden_states.is_cuda and encoder_hidden_states.dtype == torch.bfloat16)))

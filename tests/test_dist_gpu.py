@@ -58,7 +58,15 @@ def _worker(rank, world, port, q):
         same_across_ranks = [torch.zeros_like(reduced) for _ in range(world)]
         dist.all_gather(same_across_ranks, reduced)
         identical = all(torch.equal(t, reduced) for t in same_across_ranks)
-        q.put((rank, err, bool(launched_during_backward), bool(identical), float(single.abs().max())))
+        # the same step as ONE captured CUDA graph per rank (forward, backward and the chunked NCCL all-reduces on the side
+        # stream are all graph nodes): its averaged gradients equal the eager step's
+        bucket.set_overlap_enabled(True)
+        xs, ls = shard_batch(x).to(dev), shard_batch(labels).to(dev)
+        step = sar.GraphedTrainStep(w, bucket, xs, ls, warmup=2)        # check=True compares with an eager reduced step
+        step(xs, ls)
+        torch.cuda.synchronize()
+        gerr = ((bucket.buffer - reduced).abs().max() / reduced.abs().max().clamp_min(1e-12)).item()
+        q.put((rank, err, bool(launched_during_backward), bool(identical), float(single.abs().max()), gerr))
     finally:
         dist.destroy_process_group()
 
@@ -76,8 +84,9 @@ def test_nccl_allreduced_lora_grads_equal_single_gpu_grads(world):
     results = [q.get(timeout=600) for _ in range(world)]
     for p in procs:
         p.join(timeout=120)
-    for rank, err, launched, identical, gmax in sorted(results):
+    for rank, err, launched, identical, gmax, gerr in sorted(results):
         assert gmax > 0
+        assert gerr <= 2e-2, (rank, gerr)                              # graph replay vs the eager reduced step
         assert launched, "a chunk's all-reduce was not launched during backward"
         assert identical, "ranks disagree on the reduced bucket"
         # bf16 activations, fp32 reductions in a different order (per-rank partial sums, then NCCL's tree)

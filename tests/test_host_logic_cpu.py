@@ -402,3 +402,27 @@ def test_route_mix_context_and_merged_adapter_layout(micro_model):
     assert torch.equal(Bp_m[0, :, 16:32].float(), (attn.q_proj.lora_B["b"].weight * 0.125).to(torch.bfloat16).float())
     assert torch.equal(Bp_m[1, :, :16].float(), attn.v_proj.lora_B["a"].weight.to(torch.bfloat16).float())
     assert torch.count_nonzero(Bp_m[:, :, 32:]) == 0                       # rank padding
+
+
+def test_operand_refresh_descriptor_matches_the_header_and_cache_harvest_sees_every_stack():
+    """sar_refresh_desc (include/sar.h) <-> the ctypes mirror used to build the device table; cached_tensors() returns
+    every tensor a captured graph may address in a module's operand cache (GraphedTrainStep keeps them alive)."""
+    import ctypes
+    import re
+
+    from speech_adapter_routing_b200.operand_refresh import _Desc, cached_tensors
+
+    header = (Path(__file__).resolve().parents[1] / "include" / "sar.h").read_text()
+    body = re.search(r"typedef struct sar_refresh_desc \{(.*?)\} sar_refresh_desc;", header, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = [n.strip() for decl in body.split(";") if decl.strip()
+              for n in decl.replace("const ", "").replace("*", " ").split(None, 1)[1].split(",")]
+    assert fields == [n for n, _ in _Desc._fields_]
+    assert ctypes.sizeof(_Desc) == 64
+
+    m = sar.RoutedLoRALinear(nn.Linear(128, 256), "a", r=16, lora_alpha=32)
+    m.add_adapter("b", 16, 32)
+    st = m._stacks(backward=True)
+    held = {t.data_ptr() for t in cached_tensors(nn.Sequential(m))}
+    for k in ("W", "A", "Bp", "Wt", "At", "Bt"):
+        assert st[k].data_ptr() in held, k

@@ -365,3 +365,43 @@ def test_projection_with_precomputed_u_equals_the_two_launch_split_path(cuda_dev
     for a, b in zip(got, want):
         assert rel_err(a, b) <= TIGHT
     assert torch.equal(got[1], want[1])            # k_proj carries no adapter: bit-identical
+
+
+# ------------------------------------------------------------------------------------------------ operand refresh
+def test_operand_refresh_rederives_every_block_bit_exactly(cuda_dev):
+    """sar_operand_refresh: dst = bf16(scale·src) over strided / transposed blocks of padded stacks, fp32 and bf16
+    sources; padding stays untouched.  Bit-exact against the same arithmetic in torch (fp32 multiply, one rounding)."""
+    import ctypes
+
+    from speech_adapter_routing_b200 import _lib
+    from speech_adapter_routing_b200.operand_refresh import _Desc
+
+    dev = cuda_dev
+    g = torch.Generator().manual_seed(5)
+    r, rp, d_in, d_out = 12, 16, 384, 768
+    wA = torch.randn(r, d_in, generator=g).to(dev)
+    wB = (torch.randn(d_out, r, generator=g) * 0.02).to(dev)
+    wB16 = wB.to(torch.bfloat16)
+    A = torch.full((2, rp, d_in), 7.0, dtype=torch.bfloat16, device=dev)
+    Bp = torch.full((2, d_out, 64), 7.0, dtype=torch.bfloat16, device=dev)
+    At = torch.full((2, d_in, 64), 7.0, dtype=torch.bfloat16, device=dev)
+    Bt = torch.full((2, rp, d_out), 7.0, dtype=torch.bfloat16, device=dev)
+    jobs = [(wA, A[1, :r, :], 1.0), (wB, Bp[0, :, :r], 2.0), (wA.t(), At[1, :, :r], 1.0), (wB.t(), Bt[0, :r, :], 0.25),
+            (wB16, Bp[1, :, :r], 0.125), (wB16.t(), Bt[1, :r, :], 1.0)]
+    descs = []
+    for src, dst, s in jobs:
+        dt = _lib.SAR_DTYPE_F32 if src.dtype == torch.float32 else _lib.SAR_DTYPE_BF16
+        descs.append(_Desc(src.data_ptr(), dst.data_ptr(), dst.shape[0], dst.shape[1], src.stride(0), src.stride(1),
+                           dst.stride(0), dst.stride(1), s, dt))
+    table = torch.frombuffer(bytearray(bytes((_Desc * len(descs))(*descs))), dtype=torch.uint8).to(dev)
+    _lib.check(_lib.lib().sar_operand_refresh(table.data_ptr(), len(descs), max(d.numel() for _, d, _ in jobs),
+                                              torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    for src, dst, s in jobs:
+        assert torch.equal(dst, (src.float() * s).to(torch.bfloat16))
+    seven = torch.tensor(7.0, dtype=torch.bfloat16, device=dev)
+    assert (A[0] == seven).all() and (A[1, r:] == seven).all() and (Bp[:, :, r:] == seven).all()
+    assert (At[0] == seven).all() and (At[1, :, r:] == seven).all() and (Bt[:, r:] == seven).all()
+    # empty table is a no-op; a null table with entries is rejected
+    _lib.check(_lib.lib().sar_operand_refresh(None, 0, 1, torch.cuda.current_stream().cuda_stream))
+    assert _lib.lib().sar_operand_refresh(None, 3, 16, torch.cuda.current_stream().cuda_stream) == _lib.SAR_EINVAL

@@ -21,6 +21,7 @@ import torch
 
 import speech_adapter_routing_b200 as sar
 from oracle import fixtures, lora as olora, router as orouter, whisper as owhisper
+from speech_adapter_routing_b200 import ops
 
 pytestmark = pytest.mark.gpu
 
@@ -306,10 +307,16 @@ def test_module_default_and_beam_expanded_routing(cuda_dev):
             m(x)
 
 
-def test_whisper_lora_training_step_grads_match_oracle(cuda_dev, monkeypatch):
+@pytest.mark.parametrize("fused,B_", [(True, 2), (False, 2), (True, 3), (False, 3)])
+def test_whisper_lora_training_step_grads_match_oracle(cuda_dev, monkeypatch, fused, B_):
     """BASELINE config 5 shape family (single adapter, fwd + LoRA-only bwd): gradients of every lora_A / lora_B from
-    K3 through autograd equal fp32 autograd of the oracle model on the same batch."""
+    K3 through autograd equal fp32 autograd of the oracle model on the same batch — through the fused training layers
+    (whisper_train.py) and through HF's layer bodies over the K1 / K3 module slots; B_ = 3 puts the encoder's
+    projections (4500 rows) on the split LoRA path of K1 and K3."""
     monkeypatch.setenv("SAR_RANDOM_INIT", "1")
+    from speech_adapter_routing_b200 import whisper_train
+
+    monkeypatch.setattr(whisper_train, "ENABLED", fused)
     dev = cuda_dev
     w = sar.WhisperLoRA("whisper-tiny", lora_r=16, lora_alpha=32, lora_dropout=0.0, device="cuda",
                         use_gradient_checkpointing=False)
@@ -335,16 +342,21 @@ def test_whisper_lora_training_step_grads_match_oracle(cuda_dev, monkeypatch):
         def fwd(x, lin=lin, A=params[p][0], B=params[p][1]):
             return olora.lora_linear(x, lin.weight, lin.bias, A, B, 2.0)
         lin.forward = fwd
-    B_, T_dec = 2, 6
-    x = owhisper.make_input_features(B_, cfg.num_mel_bins, [0, 0], 1, seed=8)
+    T_dec = 6
+    x = owhisper.make_input_features(B_, cfg.num_mel_bins, [0] * B_, 1, seed=8)
     dec, labels = owhisper.make_decoder_inputs(B_, T_dec, cfg.vocab_size, cfg.decoder_start_token_id)
     ref_model.train(False)
     ref_loss = ref_model(input_features=x, labels=labels).loss
     ref_loss.backward()
 
     w.train()
+    calls0 = dict(whisper_train.CALLS)
     out = w(input_features=x.to(dev).to(torch.bfloat16), labels=labels.to(dev))
     out.loss.backward()
+    # the fused training layers (forward + backward of a whole layer on libsar, whisper_train.py) are what ran
+    n_fused = (cfg.encoder_layers, cfg.decoder_layers) if fused else (0, 0)
+    assert whisper_train.CALLS["encoder_layers"] - calls0["encoder_layers"] == n_fused[0]
+    assert whisper_train.CALLS["decoder_layers"] - calls0["decoder_layers"] == n_fused[1], whisper_train.REFUSED
     assert abs(out.loss.item() - ref_loss.item()) <= 2e-2 * abs(ref_loss.item())
     checked = 0
     for p, m in sar.lora_modules(hf).items():
@@ -609,3 +621,140 @@ def test_whisper_small_greedy_32_tokens_batch_8(cuda_dev, tmp_path):
     idx, _, _ = s.oracle.detect(x)
     margins, absmax = oracle_margins(s, x, want, idx)
     assert_greedy_rows(got, want, margins, absmax)
+
+
+def test_fused_training_layers_under_gradient_checkpointing_match_the_plain_run(cuda_dev, monkeypatch):
+    """HF's gradient checkpointing (the reference default, src/models/whisper_lora.py:81-83) recomputes each layer's
+    forward inside backward: with the fused training layers the first forward runs the inference body (no_grad), the
+    recompute runs the autograd Function.  Gradients must equal the non-checkpointed run's up to the rounding difference
+    between the two bodies (the inference body's LayerNorm kernel vs ATen's: 1e-2 of the largest gradient), and HF's
+    eager bodies over the K1 / K3 module slots (SAR_FUSED_TRAIN=0 equivalent) within bf16 noise."""
+    monkeypatch.setenv("SAR_RANDOM_INIT", "1")
+    from speech_adapter_routing_b200 import whisper_train
+
+    dev = cuda_dev
+    grads = {}
+    for mode in ("plain", "ckpt", "hf_bodies"):
+        torch.manual_seed(11)                       # lora_A's kaiming init draws from the global generator
+        w = sar.WhisperLoRA("whisper-tiny", lora_r=16, lora_alpha=32, lora_dropout=0.0, device="cuda",
+                            use_gradient_checkpointing=(mode == "ckpt"))
+        g = torch.Generator().manual_seed(3)
+        with torch.no_grad():
+            for m in sar.lora_modules(w.model).values():
+                m.lora_B["default"].weight.copy_((torch.randn(m.out_features, 16, generator=g) * 0.02).to(dev))
+        cfg = w.model.config
+        x = owhisper.make_input_features(3, cfg.num_mel_bins, [0, 0, 0], 1, seed=8).to(dev).to(torch.bfloat16)
+        _, labels = owhisper.make_decoder_inputs(3, 9, cfg.vocab_size, cfg.decoder_start_token_id)
+        w.train()
+        whisper_train.ENABLED = mode != "hf_bodies"
+        try:
+            loss = w(input_features=x, labels=labels.to(dev)).loss
+            loss.backward()
+        finally:
+            whisper_train.ENABLED = True
+        grads[mode] = (loss.item(), {n: p.grad.float().clone() for n, p in w.model.named_parameters() if p.grad is not None})
+    assert len(grads["plain"][1]) == 2 * 6 * cfg.encoder_layers
+    assert abs(grads["plain"][0] - grads["ckpt"][0]) <= 1e-2 * abs(grads["plain"][0])
+    for n, gp in grads["plain"][1].items():
+        assert rel_err(gp, grads["ckpt"][1][n]) <= 1e-2, n
+        gh = grads["hf_bodies"][1][n]
+        assert rel_err(gp, gh) <= 1.2e-1, n          # two independent bf16 pipelines (each within ~5e-2 of fp32 autograd)
+    assert abs(grads["plain"][0] - grads["hf_bodies"][0]) <= 1e-2 * abs(grads["hf_bodies"][0])
+
+
+def test_graphed_train_step_matches_eager_and_tracks_parameter_updates(cuda_dev, monkeypatch):
+    """GraphedTrainStep (forward + backward of the reference's training step, src/training/trainer.py:251-256, replayed
+    as one CUDA graph): gradients equal the eager step's on a NEW batch, and still do after the LoRA parameters were
+    updated in place (the graph's first node re-derives the cached bf16 operands, operand_refresh.py) — a replay
+    that kept reading the operands of capture time would fail the second comparison."""
+    monkeypatch.setenv("SAR_RANDOM_INIT", "1")
+    from speech_adapter_routing_b200 import whisper_train
+
+    dev = cuda_dev
+    torch.manual_seed(5)
+    for ckpt in (False, True):
+        w = sar.WhisperLoRA("whisper-tiny", lora_r=16, lora_alpha=32, lora_dropout=0.0, device="cuda",
+                            use_gradient_checkpointing=ckpt)
+        w.train()
+        cfg = w.model.config
+        g = torch.Generator().manual_seed(3)
+        with torch.no_grad():
+            for m in sar.lora_modules(w.model).values():
+                m.lora_B["default"].weight.copy_((torch.randn(m.out_features, 16, generator=g) * 0.02).to(dev))
+        params = [p for p in w.model.parameters() if p.requires_grad]
+        bucket = sar.FlatGradBucket(params)
+
+        def batch(seed):
+            x = owhisper.make_input_features(3, cfg.num_mel_bins, [0, 0, 0], 1, seed=seed).to(dev).to(torch.bfloat16)
+            _, labels = owhisper.make_decoder_inputs(3, 9, cfg.vocab_size, cfg.decoder_start_token_id, seed=seed)
+            return x, labels.to(dev)
+
+        def eager(x, labels):
+            bucket.zero_()
+            loss = w(input_features=x, labels=labels).loss
+            loss.backward()
+            return float(loss), bucket.buffer.clone()
+
+        x0, l0 = batch(8)
+        calls0 = dict(whisper_train.CALLS)
+        step = sar.GraphedTrainStep(w, bucket, x0, l0, warmup=2)          # check=True: compares with eager on (x0, l0)
+        assert whisper_train.CALLS["decoder_layers"] > calls0["decoder_layers"], whisper_train.REFUSED
+        assert whisper_train.REFUSED == {"encoder": "", "decoder": ""}   # the capture took the fused layers
+        x1, l1 = batch(9)
+        loss_g = float(step(x1, l1))
+        grad_g = bucket.buffer.clone()
+        loss_e, grad_e = eager(x1, l1)
+        assert rel_err(grad_g, grad_e) <= 2e-2 and abs(loss_g - loss_e) <= 2e-2 * abs(loss_e)
+        assert rel_err(grad_g, eager(x0, l0)[1]) > 5e-2                   # the two batches do differ
+        with torch.no_grad():                                             # an optimizer step's worth of change
+            for p in params:
+                p.add_(torch.randn(p.shape, generator=g).to(dev) * 0.05 * p.abs().max().clamp_min(0.02))
+        loss_e2, grad_e2 = eager(x1, l1)
+        assert rel_err(grad_e2, grad_e) > 5e-2                            # the update matters
+        loss_g2 = float(step(x1, l1))
+        assert rel_err(bucket.buffer, grad_e2) <= 2e-2 and abs(loss_g2 - loss_e2) <= 2e-2 * abs(loss_e2)
+        del step
+
+
+def test_eager_training_loop_refreshes_operands_in_one_launch_and_stays_exact(cuda_dev, monkeypatch):
+    """The reference's loop (forward, backward, optimizer.step; src/training/trainer.py:251-268) through WhisperLoRA: from
+    the third step on the stale bf16 LoRA operands are re-derived by one sar_operand_refresh launch.  The step after
+    that must equal the same step with every cache rebuilt from scratch (refresh_operands() invalidates them) — same
+    operand bits, so the only difference left is cuDNN's atomically accumulated dQ (1e-3) — and a cache rebuilt behind the
+    refresher's back must make it stand down."""
+    monkeypatch.setenv("SAR_RANDOM_INIT", "1")
+    dev = cuda_dev
+    torch.manual_seed(3)
+    w = sar.WhisperLoRA("whisper-tiny", lora_r=16, lora_alpha=32, lora_dropout=0.0, device="cuda",
+                        use_gradient_checkpointing=False)
+    w.train()
+    cfg = w.model.config
+    g = torch.Generator().manual_seed(3)
+    with torch.no_grad():
+        for m in sar.lora_modules(w.model).values():
+            m.lora_B["default"].weight.copy_((torch.randn(m.out_features, 16, generator=g) * 0.02).to(dev))
+    params = [p for p in w.model.parameters() if p.requires_grad]
+    opt = torch.optim.SGD(params, lr=0.5)
+    x = owhisper.make_input_features(2, cfg.num_mel_bins, [0, 0], 1, seed=8).to(dev).to(torch.bfloat16)
+    _, labels = owhisper.make_decoder_inputs(2, 6, cfg.vocab_size, cfg.decoder_start_token_id)
+    labels = labels.to(dev)
+
+    def grads():
+        opt.zero_grad(set_to_none=True)
+        loss = w(input_features=x, labels=labels).loss
+        loss.backward()
+        return loss.item(), [p.grad.clone() for p in params]
+
+    for _ in range(3):
+        grads()
+        opt.step()
+    assert w.__dict__["_sar_refresh"] is not None                     # built at the start of step 2, used at step 3
+    launches0 = ops.LAUNCHES.get("refresh", 0)
+    loss_a, ga = grads()                                              # operands refreshed in place by one launch
+    assert ops.LAUNCHES.get("refresh", 0) == launches0 + 1
+    sar.refresh_operands()                                            # epoch bump: every cache rebuilds from the parameters
+    loss_b, gb = grads()
+    assert w.__dict__["_sar_refresh"] is None or w.__dict__["_sar_refresh"]._frozen0 != ()   # stood down / rebuilt
+    assert loss_a == loss_b
+    for a, b in zip(ga, gb):
+        assert rel_err(a, b) <= 1e-3
