@@ -159,8 +159,15 @@ class _ProjPack:
             self._lnu_key, self._lnu_ok = key, ops.layernorm_lora_u_supported(*key)
         return self._lnu_ok
 
-    def __call__(self, x: torch.Tensor, idx: Optional[torch.Tensor], u: Optional[torch.Tensor] = None) -> List[torch.Tensor]:
+    def __call__(self, x: torch.Tensor, idx: Optional[torch.Tensor], u: Optional[torch.Tensor] = None,
+                 head_major: bool = True) -> List[torch.Tensor]:
+        """The fused projections of ``x``: one tensor per segment, [B, h, T, 64] (``head_major``) or [B, T, d_out]."""
         lora = idx is not None and self.A is not None
+        if not head_major:                      # training layers: row-major outputs viewed as heads without a copy
+            return ops.attn_proj_fwd(x, self.W, self.bias, self.A if lora else None, self.Bp if lora else None,
+                                     idx if lora else None, self.seg_set if lora else [-1] * len(self.seg_set),
+                                     self.kernel_scale, self.n_sets if lora else 1, self.scale, y_head_major=False,
+                                     u=u if lora else None)
         B, T, d = x.shape
         mix = current_mix_weights() if lora else None
         if mix is not None:
@@ -535,13 +542,21 @@ def _lm_head_forward(self, x: torch.Tensor) -> torch.Tensor:
     live in a buffer whose row stride is padded to 8 elements and the returned tensor is the [.., :V] view of it."""
     W = self.weight
     if not (FUSED_BLOCKS_ENABLED and x.is_cuda and x.dtype == torch.bfloat16 and W.dtype == torch.bfloat16
-            and self.bias is None and not torch.is_grad_enabled() and W.is_contiguous() and x.shape[-1] % 8 == 0):
+            and self.bias is None and W.is_contiguous() and x.shape[-1] % 8 == 0):
         return self._sar_hf_forward(x)
     d = x.shape[-1]
     M = x.numel() // d
     V = W.shape[0]
     ldy = (V + 7) // 8 * 8
     x2 = x.contiguous().view(M, d)
+    if torch.is_grad_enabled() and (x.requires_grad or W.requires_grad):
+        from . import whisper_train
+
+        if W.requires_grad or not whisper_train.ENABLED:
+            return self._sar_hf_forward(x)
+        # training: the same launch under autograd; the [.., :V] slice below is an ordinary view op, so its backward hands
+        # the Function a zero-padded [M, ldy] gradient that the dX GEMM reads with 16-byte aligned rows
+        return whisper_train.lm_head_train(x2, self, ldy).view(*x.shape[:-1], ldy)[..., :V]
     buf = torch.empty(M, ldy, dtype=torch.bfloat16, device=x.device)
     ops.dense_fwd(x2, d, 0, W.detach(), None, buf, ldy, 0, 1, M, d, V)
     return buf.view(*x.shape[:-1], ldy)[..., :V]

@@ -24,10 +24,11 @@ import torch.nn.functional as F
 from . import ops
 from ._lib import SAR_ACT_NONE
 from .lora_linear import RoutedLoRALinear, _notify_grad_ready
+from .routing import current_mix_weights
 
 ENABLED = __import__("os").environ.get("SAR_FUSED_TRAIN", "1") != "0"
-# softmax(QKᵀ)V forward / backward: "cudnn" and "flash" call ATen's fused-attention ops directly (no nested autograd
-# graph, so the step is CUDA-graph capturable and costs one host call each way); "autograd" differentiates F.sdpa.
+# softmax(QKᵀ)V forward / backward: "cudnn" or "flash" — ATen's fused-attention ops, called directly (no nested autograd
+# graph: one host call each way, CUDA-graph capturable, and every saved tensor can go through ctx.save_for_backward).
 SDPA_IMPL = __import__("os").environ.get("SAR_TRAIN_SDPA", "cudnn")
 # Set by train_graph.GraphedTrainStep around its calls: under CUDA-graph capture HF materialises the decoder's causal mask
 # as a tensor instead of passing None (transformers/masking_utils.py:262-275 refuses to skip it while "tracing"); the
@@ -141,108 +142,115 @@ def _lora_bwd(m: RoutedLoRALinear, dy: torch.Tensor, x: torch.Tensor, u: torch.T
     return dx, grads
 
 
-class _Attn:
-    """Forward of one attention (projections on the fused kernel, SDPA under a private autograd graph) that keeps what
-    the backward needs."""
+# Tensors one attention keeps for its backward, in save order.  They all travel through ctx.save_for_backward, so under
+# HF's gradient checkpointing (non-reentrant: the first forward runs with grad enabled) the saved-tensor hooks really drop
+# them and the recompute really refills them — Python attributes on ctx would keep every activation alive.
+_ATTN_FIELDS = ("x_q", "x_kv", "u_q", "u_kv", "q", "k", "v", "o", "lse", "cq", "ck", "seed", "off")
+_N_ATTN = len(_ATTN_FIELDS)
 
-    def __init__(self, proj_q, proj_kv, out_pack, x_q, x_kv, idx, causal: bool):
-        # proj_q: _ProjPack producing q (and k, v when proj_kv is None: self-attention); proj_kv: cross-attention k | v
-        self.proj_q, self.proj_kv, self.out_pack, self.causal = proj_q, proj_kv, out_pack, causal
-        self.x_q, self.x_kv, self.idx = x_q, x_kv, idx
-        self.u_q = self._u(proj_q, x_q)
-        ys = proj_q(x_q, idx if proj_q.lora_mods else None, u=self.u_q)
-        if proj_kv is None:
-            q, k, v = ys
-            self.u_kv = None
+
+def _heads(t: torch.Tensor, H: int) -> torch.Tensor:
+    """[B, T, d] -> [B, h, T, 64] strided view (HF's own q / k / v layout: no copy in either direction)."""
+    B, T, d = t.shape
+    return t.view(B, T, H, d // H).transpose(1, 2)
+
+
+def _lora_u(proj, x, idx):
+    """U = scale·x·A_kᵀ planes of one fused projection call ([n_sets, B, T, r]): the forward's low-rank operand and K3's
+    ``u``."""
+    if idx is None or proj.A is None:
+        return None
+    return ops.lora_u_fwd(x, proj.A, idx, proj.n_sets, proj.scale, proj.W.shape[0] // len(proj.mods))
+
+
+def _sdpa_fwd(q, k, v, is_causal: bool):
+    """softmax(QKᵀ)V on ATen's fused-attention ops, called directly (one host call, CUDA-graph capturable).  Returns
+    (o, [lse, cum_seq_q, cum_seq_k, seed, offset], (kind, max_q, max_k))."""
+    global SDPA_IMPL
+    aten = torch.ops.aten
+    if SDPA_IMPL == "cudnn":
+        try:
+            r = aten._scaled_dot_product_cudnn_attention(q, k, v, None, True, 0.0, is_causal, False, scale=1.0)
+            return r[0], [r[1], r[2], r[3], r[6], r[7]], ("cudnn", r[4], r[5])
+        except (RuntimeError, TypeError):
+            SDPA_IMPL = "flash"               # this build / shape has no cuDNN attention: ATen's flash kernels
+    r = aten._scaled_dot_product_flash_attention(q, k, v, 0.0, is_causal, False, scale=1.0)
+    return r[0], [r[1], r[2], r[3], r[6], r[7]], ("flash", r[4], r[5])
+
+
+def _sdpa_bwd(do, q, k, v, o, lse, cq, ck, seed, off, meta, is_causal: bool):
+    aten = torch.ops.aten
+    kind, mq, mk = meta
+    if kind == "cudnn":
+        return aten._scaled_dot_product_cudnn_attention_backward(do, q, k, v, o, lse, seed, off, None, cq, ck, mq, mk, 0.0,
+                                                                 is_causal, scale=1.0)
+    return aten._scaled_dot_product_flash_attention_backward(do, q, k, v, o, lse, cq, ck, mq, mk, 0.0, is_causal, seed, off,
+                                                             scale=1.0)
+
+
+def _attn_fwd(proj_q, proj_kv, out_pack, x_q, x_kv, idx, causal: bool, residual: torch.Tensor, H: int):
+    """One attention block of a layer: fused projections (row-major outputs, viewed as heads without a copy), SDPA,
+    out_proj + residual.  proj_q produces q (and k, v when proj_kv is None: self-attention); proj_kv the cross-attention
+    k | v from ``x_kv``.  Returns (h_out, saved tensors in _ATTN_FIELDS order, meta)."""
+    u_q = _lora_u(proj_q, x_q, idx)
+    ys = proj_q(x_q, idx if proj_q.lora_mods else None, u=u_q, head_major=False)
+    u_kv = None
+    if proj_kv is None:
+        q, k, v = ys
+    else:
+        (q,) = ys
+        u_kv = _lora_u(proj_kv, x_kv, idx)
+        k, v = proj_kv(x_kv, idx if proj_kv.lora_mods else None, u=u_kv, head_major=False)
+    is_causal = causal and q.shape[1] > 1
+    o, extra, meta = _sdpa_fwd(_heads(q, H), _heads(k, H), _heads(v, H), is_causal)
+    _trace("attn.fwd u_q,u_kv,q,k,v,o", u_q, u_kv, q, k, v, o)
+    p = out_pack.get()
+    out = ops.linear_fwd(_to_rows(o), p.W, p.b, residual, SAR_ACT_NONE)
+    return out, [x_q, x_kv, u_q, u_kv, q, k, v, o] + extra, (meta, is_causal, H)
+
+
+def _proj_bwd(proj, x, u, idx, dys: List[torch.Tensor]):
+    """dX and the LoRA gradients of one fused projection call.  ``dys``: row-major output gradients per segment."""
+    dx = None
+    grads: List[Optional[torch.Tensor]] = []
+    set_i = 0
+    for m, s, dy in zip(proj.mods, proj.seg_scale, dys):
+        if s != 1.0:
+            dy = dy * s                          # q = s·(x Wᵀ + b + Δ): the scale sits outside the projection
+        lora = isinstance(m, RoutedLoRALinear) and bool(m.adapter_order)
+        if lora and idx is not None:
+            B, T, _ = x.shape
+            part, g = _lora_bwd(m, dy, x, u[set_i].reshape(B * T, -1), idx)
+            grads += g
+            set_i += 1
         else:
-            (q,) = ys
-            self.u_kv = self._u(proj_kv, x_kv)
-            k, v = proj_kv(x_kv, idx if proj_kv.lora_mods else None, u=self.u_kv)
-        self.is_causal = causal and q.shape[2] > 1
-        self._sdpa_fwd(q, k, v)
-        _trace("attn.fwd u_q,u_kv,q,k,v,o", self.u_q, self.u_kv, q, k, v, self.o)
+            if lora:                             # adapters present but switched off for this call: no gradient
+                grads += [None] * (2 * len(m.adapter_order))
+            base = m.base_layer if isinstance(m, RoutedLoRALinear) else m
+            packs = proj.__dict__.setdefault("_dx_packs", {})
+            pack = packs.get(id(m))
+            if pack is None:
+                pack = packs[id(m)] = _WtPack(base)
+            part = _dense_dx(dy.contiguous(), pack)
+        dx = part if dx is None else dx + part
+    return dx, grads
 
-    def _sdpa_fwd(self, q, k, v) -> None:
-        global SDPA_IMPL
-        aten = torch.ops.aten
-        if SDPA_IMPL == "cudnn":
-            try:
-                r = aten._scaled_dot_product_cudnn_attention(q, k, v, None, True, 0.0, self.is_causal, False, scale=1.0)
-                self.q, self.k, self.v, self.o, self.sdpa = q, k, v, r[0], ("cudnn",) + tuple(r[1:8])
-                return
-            except (RuntimeError, TypeError):
-                SDPA_IMPL = "flash"               # this build / shape has no cuDNN attention: ATen's flash kernels
-        if SDPA_IMPL == "flash":
-            r = aten._scaled_dot_product_flash_attention(q, k, v, 0.0, self.is_causal, False, scale=1.0)
-            self.q, self.k, self.v, self.o, self.sdpa = q, k, v, r[0], ("flash",) + tuple(r[1:8])
-            return
-        with torch.enable_grad():
-            self.q, self.k, self.v = (t.detach().requires_grad_(True) for t in (q, k, v))
-            self.o = F.scaled_dot_product_attention(self.q, self.k, self.v, is_causal=self.is_causal, scale=1.0)
-            self.sdpa = ("autograd",)
 
-    def _sdpa_bwd(self, do: torch.Tensor):
-        aten = torch.ops.aten
-        kind = self.sdpa[0]
-        if kind == "autograd":
-            return torch.autograd.grad(self.o, (self.q, self.k, self.v), do)
-        lse, cq, ck, mq, mk, seed, off = self.sdpa[1:]
-        if kind == "cudnn":
-            return aten._scaled_dot_product_cudnn_attention_backward(do, self.q, self.k, self.v, self.o, lse, seed, off,
-                                                                     None, cq, ck, mq, mk, 0.0, self.is_causal, scale=1.0)
-        return aten._scaled_dot_product_flash_attention_backward(do, self.q, self.k, self.v, self.o, lse, cq, ck, mq, mk,
-                                                                 0.0, self.is_causal, seed, off, scale=1.0)
-
-    def _u(self, proj, x):
-        """U = scale·x·A_kᵀ planes for this call ([n_sets, B, T, r]) — the forward's low-rank operand and K3's ``u``."""
-        if self.idx is None or proj.A is None:
-            return None
-        return ops.lora_u_fwd(x, proj.A, self.idx, proj.n_sets, proj.scale, proj.W.shape[0] // len(proj.mods))
-
-    def out(self, residual: torch.Tensor) -> torch.Tensor:
-        p = self.out_pack.get()
-        return ops.linear_fwd(self.o.detach(), p.W, p.b, residual, SAR_ACT_NONE, x_head_major=True)
-
-    def _proj_bwd(self, proj, x, u, dys_hm: List[torch.Tensor]):
-        """dX and the LoRA gradients of one fused projection call.  ``dys_hm``: head-major output gradients per segment."""
-        dx = None
-        grads: List[Optional[torch.Tensor]] = []
-        set_i = 0
-        for m, s, dy_hm in zip(proj.mods, proj.seg_scale, dys_hm):
-            dy = _to_rows(dy_hm)
-            if s != 1.0:
-                dy = dy * s                      # q = s·(x Wᵀ + b + Δ): the scale sits outside the projection
-            lora = isinstance(m, RoutedLoRALinear) and bool(m.adapter_order)
-            if lora and self.idx is not None:
-                B, T, _ = x.shape
-                part, g = _lora_bwd(m, dy, x, u[set_i].reshape(B * T, -1), self.idx)
-                grads += g
-                set_i += 1
-            else:
-                if lora:                             # adapters present but switched off for this call: no gradient
-                    grads += [None] * (2 * len(m.adapter_order))
-                base = m.base_layer if isinstance(m, RoutedLoRALinear) else m
-                packs = proj.__dict__.setdefault("_dx_packs", {})
-                pack = packs.get(id(m))
-                if pack is None:
-                    pack = packs[id(m)] = _WtPack(base)
-                part = _dense_dx(dy, pack)
-            dx = part if dx is None else dx + part
-        return dx, grads
-
-    def backward(self, dh_out: torch.Tensor):
-        """dh_out: gradient of out_proj's output (the residual branch is handled by the caller).  Returns
-        (dx_q, dx_kv, lora grads of proj_q, lora grads of proj_kv)."""
-        H = self.q.shape[1]
-        do = _to_heads(_dense_dx(dh_out, self.out_pack), H)
-        dq, dk, dv = self._sdpa_bwd(do)
-        _trace("attn.bwd do,dq,dk,dv", do, dq, dk, dv)
-        if self.proj_kv is None:
-            dx, g = self._proj_bwd(self.proj_q, self.x_q, self.u_q, [dq, dk, dv])
-            return dx, None, g, []
-        dxq, gq = self._proj_bwd(self.proj_q, self.x_q, self.u_q, [dq])
-        dxkv, gkv = self._proj_bwd(self.proj_kv, self.x_kv, self.u_kv, [dk, dv])
-        return dxq, dxkv, gq, gkv
+def _attn_bwd(proj_q, proj_kv, out_pack, idx, saved, meta, dh_out: torch.Tensor):
+    """dh_out: gradient of out_proj's output (the residual branch is the caller's).  Returns (dx_q, dx_kv, LoRA grads of
+    proj_q, LoRA grads of proj_kv)."""
+    x_q, x_kv, u_q, u_kv, q, k, v, o, lse, cq, ck, seed, off = saved
+    sd_meta, is_causal, H = meta
+    do = _to_heads(_dense_dx(dh_out, out_pack), H)
+    dq, dk, dv = _sdpa_bwd(do, _heads(q, H), _heads(k, H), _heads(v, H), o, lse, cq, ck, seed, off, sd_meta, is_causal)
+    _trace("attn.bwd do,dq,dk,dv", do, dq, dk, dv)
+    dq, dk, dv = _to_rows(dq), _to_rows(dk), _to_rows(dv)
+    if proj_kv is None:
+        dx, g = _proj_bwd(proj_q, x_q, u_q, idx, [dq, dk, dv])
+        return dx, None, g, []
+    dxq, gq = _proj_bwd(proj_q, x_q, u_q, idx, [dq])
+    dxkv, gkv = _proj_bwd(proj_kv, x_kv, u_kv, idx, [dk, dv])
+    return dxq, dxkv, gq, gkv
 
 
 class _WtPack:
@@ -264,6 +272,7 @@ class _WtPack:
 
 
 def _ffn_fwd(layer, pk, h: torch.Tensor):
+    """LayerNorm -> fc1 -> GELU -> fc2 + residual.  Saved: (h, mean, rstd, pre-activation)."""
     x3, mean3, rstd3 = _ln_fwd(h, layer.final_layer_norm)
     p1, p2 = pk["fc1"].get(), pk["fc2"].get()
     B, T, d = h.shape
@@ -312,23 +321,24 @@ class _EncoderLayerFn(torch.autograd.Function):
     def forward(ctx, h, layer, idx, *lora_ws):
         pk = layer._sar_pack
         h = h.contiguous()
+        H = layer.self_attn.num_heads
         x1, mean1, rstd1 = _ln_fwd(h, layer.self_attn_layer_norm)
-        attn = _Attn(pk["self"].qkv.get(), None, pk["self"].out, x1, None, idx, causal=False)
-        h2 = attn.out(h)
+        h2, sa, sa_meta = _attn_fwd(pk["self"].qkv.get(), None, pk["self"].out, x1, None, idx, False, h, H)
         out, ffn_saved = _ffn_fwd(layer, pk, h2)
-        ctx.layer, ctx.attn, ctx.ffn_saved, ctx.n_ws = layer, attn, ffn_saved, len(lora_ws)
-        ctx.save_for_backward(h, mean1, rstd1)
+        ctx.layer, ctx.idx, ctx.sa_meta, ctx.n_ws = layer, idx, sa_meta, len(lora_ws)
+        ctx.save_for_backward(h, mean1, rstd1, *sa, *ffn_saved)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        layer, attn = ctx.layer, ctx.attn
+        layer = ctx.layer
         pk = layer._sar_pack
-        h, mean1, rstd1 = ctx.saved_tensors
-        dh2 = _ffn_bwd(layer, pk, ctx.ffn_saved, dout.contiguous())
-        dx1, _, g, _ = attn.backward(dh2)
+        t = ctx.saved_tensors
+        h, mean1, rstd1 = t[:3]
+        sa, ffn_saved = t[3:3 + _N_ATTN], t[3 + _N_ATTN:]
+        dh2 = _ffn_bwd(layer, pk, ffn_saved, dout.contiguous())
+        dx1, _, g, _ = _attn_bwd(pk["self"].qkv.get(), None, pk["self"].out, ctx.idx, sa, ctx.sa_meta, dh2)
         dh = dh2 + _ln_bwd(dx1, h, mean1, rstd1, layer.self_attn_layer_norm)
-        ctx.attn = ctx.ffn_saved = None
         return (dh, None, None, *_weight_grads(ctx, g))
 
 
@@ -338,32 +348,77 @@ class _DecoderLayerFn(torch.autograd.Function):
         pk = layer._sar_pack
         h = h.contiguous()
         enc = enc.contiguous()
+        H = layer.self_attn.num_heads
         x1, mean1, rstd1 = _ln_fwd(h, layer.self_attn_layer_norm)
-        sa = _Attn(pk["self"].qkv.get(), None, pk["self"].out, x1, None, idx, causal=True)
-        h2 = sa.out(h)
+        h2, sa, sa_meta = _attn_fwd(pk["self"].qkv.get(), None, pk["self"].out, x1, None, idx, True, h, H)
         x2, mean2, rstd2 = _ln_fwd(h2, layer.encoder_attn_layer_norm)
-        ca = _Attn(pk["cross"].q.get(), pk["cross"].kv.get(), pk["cross"].out, x2, enc, idx, causal=False)
-        h3 = ca.out(h2)
+        h3, ca, ca_meta = _attn_fwd(pk["cross"].q.get(), pk["cross"].kv.get(), pk["cross"].out, x2, enc, idx, False, h2, H)
         out, ffn_saved = _ffn_fwd(layer, pk, h3)
         _trace("dec.fwd h,enc,h2,h3,out", h, enc, h2, h3, out)
-        ctx.layer, ctx.sa, ctx.ca, ctx.ffn_saved, ctx.n_ws = layer, sa, ca, ffn_saved, len(lora_ws)
-        ctx.save_for_backward(h, mean1, rstd1, h2, mean2, rstd2)
+        ctx.layer, ctx.idx, ctx.sa_meta, ctx.ca_meta, ctx.n_ws = layer, idx, sa_meta, ca_meta, len(lora_ws)
+        ctx.save_for_backward(h, mean1, rstd1, h2, mean2, rstd2, *sa, *ca, *ffn_saved)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        layer, sa, ca = ctx.layer, ctx.sa, ctx.ca
+        layer = ctx.layer
         pk = layer._sar_pack
-        h, mean1, rstd1, h2, mean2, rstd2 = ctx.saved_tensors
-        dh3 = _ffn_bwd(layer, pk, ctx.ffn_saved, dout.contiguous())
-        dx2, denc, gq, gkv = ca.backward(dh3)
+        t = ctx.saved_tensors
+        h, mean1, rstd1, h2, mean2, rstd2 = t[:6]
+        sa, ca, ffn_saved = t[6:6 + _N_ATTN], t[6 + _N_ATTN:6 + 2 * _N_ATTN], t[6 + 2 * _N_ATTN:]
+        dh3 = _ffn_bwd(layer, pk, ffn_saved, dout.contiguous())
+        dx2, denc, gq, gkv = _attn_bwd(pk["cross"].q.get(), pk["cross"].kv.get(), pk["cross"].out, ctx.idx, ca, ctx.ca_meta,
+                                       dh3)
         _trace("dec.bwd dout,dh3,dx2,denc", dout, dh3, dx2, denc)
         dh2 = dh3 + _ln_bwd(dx2, h2, mean2, rstd2, layer.encoder_attn_layer_norm)
-        dx1, _, gs, _ = sa.backward(dh2)
+        dx1, _, gs, _ = _attn_bwd(pk["self"].qkv.get(), None, pk["self"].out, ctx.idx, sa, ctx.sa_meta, dh2)
         dh = dh2 + _ln_bwd(dx1, h, mean1, rstd1, layer.self_attn_layer_norm)
         _trace("dec.bwd dh2,dx1,dh", dh2, dx1, dh)
-        ctx.sa = ctx.ca = ctx.ffn_saved = None
         return (dh, denc, None, None, *_weight_grads(ctx, [*gs, *gq, *gkv]))
+
+
+# ------------------------------------------------------------------------------------------------ LM head
+class _LMHeadFn(torch.autograd.Function):
+    """logits = x·Eᵀ with the frozen (tied) embedding E [V, d] ($HF/modeling_whisper.py:1135 proj_out): forward and dX on the
+    pair kernel's dense entry.  V = 51865 is odd: logits and their gradient live in buffers whose row stride is padded to 8
+    elements (TMA needs 16-byte aligned rows); the caller slices the pad columns off, so their gradient arrives as zeros."""
+
+    @staticmethod
+    def forward(ctx, x2, head, ldy):
+        W = head.weight.detach()
+        M, d = x2.shape
+        buf = torch.empty(M, ldy, dtype=torch.bfloat16, device=x2.device)
+        ops.dense_fwd(x2, d, 0, W, None, buf, ldy, 0, 1, M, d, W.shape[0])   # pad columns: never read (sliced off)
+        ctx.head, ctx.d = head, d
+        return buf
+
+    @staticmethod
+    def backward(ctx, dbuf):
+        head = ctx.head
+        M, ldy = dbuf.shape
+        Wt = _lm_head_wt(head, ldy)                                   # [d, ldy] = Eᵀ, zero pad columns
+        dx = torch.empty(M, ctx.d, dtype=torch.bfloat16, device=dbuf.device)
+        ops.dense_fwd(dbuf.contiguous(), ldy, 0, Wt, None, dx, ctx.d, 0, 1, M, ldy, ctx.d)
+        return dx, None, None
+
+
+def _lm_head_wt(head, ldy: int) -> torch.Tensor:
+    from .whisper_blocks import _pver
+
+    key = (_pver(head.weight), ldy)
+    c = head.__dict__.get("_sar_wt")
+    if c is None or c[0] != key:
+        W = head.weight.detach()
+        Wt = torch.zeros(W.shape[1], ldy, dtype=torch.bfloat16, device=W.device)
+        Wt[:, : W.shape[0]] = W.t()
+        c = (key, Wt)
+        head.__dict__["_sar_wt"] = c
+    return c[1]
+
+
+def lm_head_train(x2: torch.Tensor, head, ldy: int) -> torch.Tensor:
+    CALLS["lm_head"] = CALLS.get("lm_head", 0) + 1
+    return _LMHeadFn.apply(x2, head, ldy)
 
 
 # ------------------------------------------------------------------------------------------------ entry points
@@ -375,6 +430,8 @@ def _train_refusal(layer, h: torch.Tensor, kwargs) -> str:
 
     if not (ENABLED and FUSED_BLOCKS_ENABLED):
         return "switched off"
+    if current_mix_weights() is not None:
+        return "soft_fused mix weights active (inference only)"
     if not (h.is_cuda and h.dtype == torch.bfloat16 and h.dim() == 3 and h.shape[-1] % 128 == 0):
         return f"hidden states {tuple(h.shape)} {h.dtype} {h.device.type}"
     if kwargs.get("output_attentions", False):

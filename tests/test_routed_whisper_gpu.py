@@ -357,6 +357,7 @@ def test_whisper_lora_training_step_grads_match_oracle(cuda_dev, monkeypatch, fu
     n_fused = (cfg.encoder_layers, cfg.decoder_layers) if fused else (0, 0)
     assert whisper_train.CALLS["encoder_layers"] - calls0["encoder_layers"] == n_fused[0]
     assert whisper_train.CALLS["decoder_layers"] - calls0["decoder_layers"] == n_fused[1], whisper_train.REFUSED
+    assert whisper_train.CALLS.get("lm_head", 0) - calls0.get("lm_head", 0) == (1 if fused else 0)
     assert abs(out.loss.item() - ref_loss.item()) <= 2e-2 * abs(ref_loss.item())
     checked = 0
     for p, m in sar.lora_modules(hf).items():
@@ -720,7 +721,7 @@ def test_eager_training_loop_refreshes_operands_in_one_launch_and_stays_exact(cu
     """The reference's loop (forward, backward, optimizer.step; src/training/trainer.py:251-268) through WhisperLoRA: from
     the third step on the stale bf16 LoRA operands are re-derived by one sar_operand_refresh launch.  The step after
     that must equal the same step with every cache rebuilt from scratch (refresh_operands() invalidates them) — same
-    operand bits, so the only difference left is cuDNN's atomically accumulated dQ (1e-3) — and a cache rebuilt behind the
+    operand bits, so the only difference left is cuDNN's atomically accumulated dQ (5e-3) — and a cache rebuilt behind the
     refresher's back must make it stand down."""
     monkeypatch.setenv("SAR_RANDOM_INIT", "1")
     dev = cuda_dev
@@ -757,4 +758,4 @@ def test_eager_training_loop_refreshes_operands_in_one_launch_and_stays_exact(cu
     assert w.__dict__["_sar_refresh"] is None or w.__dict__["_sar_refresh"]._frozen0 != ()   # stood down / rebuilt
     assert loss_a == loss_b
     for a, b in zip(ga, gb):
-        assert rel_err(a, b) <= 1e-3
+        assert rel_err(a, b) <= 5e-3
