@@ -20,6 +20,11 @@ ncu --nvtx --nvtx-include "timed/" --metrics gpu__time_duration.sum --clock-cont
     --log-file $OUT/r02_launch_list_one_step.csv $PY bench.py --steps 1 --warmup 3 --skip-cpu-baseline --extras none \
     > $OUT/r02_launch_list_ncu.log 2>&1
 
+# 2b. K3 alone at the training shapes: whole-call event time + per-launch durations
+$PY tools/prof_k3.py > $OUT/r02_k3_plain.log 2>&1 || { echo "prof_k3 failed"; exit 1; }
+ncu --metrics gpu__time_duration.sum --clock-control none --csv -k regex:"k1v2|k1_qv|k3_" --log-file $OUT/r02_k3_launches.csv \
+    $PY tools/prof_k3.py > $OUT/r02_k3_ncu.log 2>&1
+
 # 3. the attention kernel and the encoder SDPA beside it
 $PY tools/dev_check.py attn > $OUT/r02_attn_devcheck.log 2>&1
 
