@@ -168,9 +168,18 @@ class _OverlappedAllReduce:
         self.reset()
         from . import lora_linear
 
-        lora_linear.GRAD_READY_LISTENERS.append(self._ready)          # gradients K3 wrote in place
+        import weakref
+
+        lora_linear.GRAD_READY_LISTENERS.append(weakref.WeakMethod(self._ready))   # gradients K3 wrote in place
+        me = weakref.ref(self)
+
+        def hook(q):
+            o = me()
+            if o is not None:
+                o._ready((q,))
+
         for p in bucket.params:                                       # gradients autograd accumulated
-            p.register_post_accumulate_grad_hook(lambda q: self._ready((q,)))
+            p.register_post_accumulate_grad_hook(hook)
 
     def reset(self) -> None:
         n = len(self.param_bounds) - 1

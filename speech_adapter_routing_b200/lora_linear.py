@@ -76,12 +76,21 @@ class _QVLoRAFn(torch.autograd.Function):
 
 # Parameters whose gradient K3 wrote in place tell whoever registered here (dist.FlatGradBucket's overlapped all-reduce):
 # autograd's AccumulateGrad — and with it every post-accumulate hook — never runs for them.
-GRAD_READY_LISTENERS: List = []
+GRAD_READY_LISTENERS: List = []      # callables or weakref.WeakMethod objects (dead ones are dropped on the next notification)
 
 
 def _notify_grad_ready(*params) -> None:
-    for fn in GRAD_READY_LISTENERS:
-        fn(params)
+    import weakref
+
+    dead = False
+    for ref in GRAD_READY_LISTENERS:
+        fn = ref() if isinstance(ref, weakref.WeakMethod) else ref
+        if fn is None:
+            dead = True
+        else:
+            fn(params)
+    if dead:
+        GRAD_READY_LISTENERS[:] = [r for r in GRAD_READY_LISTENERS if not (isinstance(r, weakref.WeakMethod) and r() is None)]
 
 
 class RoutedLoRALinear(nn.Module):
