@@ -58,9 +58,8 @@ def _worker(rank, world, port, q):
         same_across_ranks = [torch.zeros_like(reduced) for _ in range(world)]
         dist.all_gather(same_across_ranks, reduced)
         identical = all(torch.equal(t, reduced) for t in same_across_ranks)
-        # the same step as ONE captured CUDA graph per rank (forward, backward and the chunked NCCL all-reduces on the side
-        # stream are all graph nodes): its averaged gradients equal the eager step's
-        bucket.set_overlap_enabled(True)
+        # the same local step as ONE captured CUDA graph per rank, the flat bucket all-reduced by one NCCL call after each
+        # replay: its averaged gradients equal the eager step's
         xs, ls = shard_batch(x).to(dev), shard_batch(labels).to(dev)
         step = sar.GraphedTrainStep(w, bucket, xs, ls, warmup=2)        # check=True compares with an eager reduced step
         step(xs, ls)
@@ -81,9 +80,13 @@ def test_nccl_allreduced_lora_grads_equal_single_gpu_grads(world):
     procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
     for p in procs:
         p.start()
-    results = [q.get(timeout=600) for _ in range(world)]
-    for p in procs:
-        p.join(timeout=120)
+    try:
+        results = [q.get(timeout=300) for _ in range(world)]
+    finally:
+        for p in procs:
+            p.join(timeout=30)
+            if p.is_alive():                 # a rank stuck in a collective must not hang the suite
+                p.kill()
     for rank, err, launched, identical, gmax, gerr in sorted(results):
         assert gmax > 0
         assert gerr <= 2e-2, (rank, gerr)                              # graph replay vs the eager reduced step
