@@ -96,8 +96,8 @@ class WhisperLoRA(nn.Module):
         """Training loop (src/training/trainer.py:251-268): after ``optimizer.step()`` the kernels' cached bf16 LoRA
         operands are stale.  From the third step on they are re-derived by ONE launch (operand_refresh.py) instead of the
         per-module host-side rebuild (~25 small kernels for each of the 72 LoRA'd projections and 48 fused calls)."""
-        if not input_features.is_cuda:
-            return
+        if not input_features.is_cuda or torch.cuda.is_current_stream_capturing():
+            return                          # a captured step carries its own refresh node (train_graph.py)
         d = self.__dict__
         r = d.get("_sar_refresh")
         if r is not None:
