@@ -9,7 +9,7 @@ from __future__ import annotations
 import ctypes
 import os
 import subprocess
-from ctypes import c_char_p, c_float, c_int, c_int32, c_int64, c_uint32, c_void_p
+from ctypes import c_char_p, c_float, c_int, c_int64, c_uint32, c_void_p
 from pathlib import Path
 
 CSRC_DIR = Path(__file__).resolve().parent / "csrc"

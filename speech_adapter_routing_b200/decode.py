@@ -18,7 +18,7 @@ short-form greedy case — anything else is delegated to HF's own loop over the 
 """
 from __future__ import annotations
 
-from typing import Dict, List, NamedTuple, Optional, Sequence
+from typing import Dict, List, NamedTuple, Optional
 
 import torch
 
