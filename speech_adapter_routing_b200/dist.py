@@ -192,9 +192,19 @@ class _OverlappedAllReduce:
         return self.enabled and dist.is_initialized() and dist.get_world_size(self.group) > 1
 
     def _ready(self, params) -> None:
+        if not self.enabled:            # switched off (local reference step, or an early micro-step of an accumulation)
+            return
         for p in params:
             i = self.b._index.get(id(p))
-            if i is None or i in self.seen:
+            if i is None:
+                continue
+            if i in self.seen:
+                if self._active() and self.launched[self.chunk_of[i]]:
+                    # a second backward since zero_() (gradient accumulation): this chunk has already been summed over
+                    # the ranks, a later local gradient on top of it would never be reduced
+                    raise RuntimeError("FlatGradBucket: a gradient arrived for a chunk that was already all-reduced in this "
+                                       "step. With gradient accumulation call set_overlap_enabled(False) for all but the "
+                                       "last micro-step (and zero_() once per optimizer step).")
                 continue
             self.seen.add(i)
             c = self.chunk_of[i]

@@ -138,6 +138,32 @@ def _overlap_worker(rank, world, port, q):
                 h = torch.tanh(h @ r_.t() @ r_)
             (h.pow(2).sum() / 4).backward()
             ok = ok and all(torch.allclose(p_.grad, r_.grad, atol=1e-5) for p_, r_ in zip(ps, refs))
+        # gradient accumulation: a second backward without zero_() must not silently stack local gradients on chunks that
+        # were already reduced; with the overlap switched off for the first micro-step it works
+        h = xs
+        for p_ in ps:
+            h = torch.tanh(h @ p_.t() @ p_)
+        try:
+            h.sum().backward()
+            ok = False
+        except RuntimeError as e:
+            ok = ok and "gradient accumulation" in str(e)
+        bucket.zero_()
+        bucket.set_overlap_enabled(False)
+        for micro in range(2):
+            if micro == 1:
+                bucket.set_overlap_enabled(True)
+            h = xs
+            for p_ in ps:
+                h = torch.tanh(h @ p_.t() @ p_)
+            (h.pow(2).sum() / 4 * world).backward()
+        bucket.finish_overlap()
+        refs = [p_.detach().clone().requires_grad_(True) for p_ in ps]
+        h = x
+        for r_ in refs:
+            h = torch.tanh(h @ r_.t() @ r_)
+        (2 * h.pow(2).sum() / 4).backward()
+        ok = ok and all(torch.allclose(p_.grad, r_.grad, atol=1e-5) for p_, r_ in zip(ps, refs))
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
