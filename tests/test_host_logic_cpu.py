@@ -426,3 +426,37 @@ def test_operand_refresh_descriptor_matches_the_header_and_cache_harvest_sees_ev
     held = {t.data_ptr() for t in cached_tensors(nn.Sequential(m))}
     for k in ("W", "A", "Bp", "Wt", "At", "Bt"):
         assert st[k].data_ptr() in held, k
+
+
+def test_training_layer_inputs_follow_where_the_gradients_go():
+    """whisper_train._fn_inputs: when K3 writes every LoRA gradient of a layer straight into the flat bucket the weights
+    are not autograd inputs of the layer Function (no AccumulateGrad nodes, CUDA-graph capture does not depend on older
+    autograd graphs); a zero-size leaf keeps a layer whose activation input needs no gradient differentiable; otherwise
+    the weights are passed and _weight_grads returns one gradient per weight."""
+    from speech_adapter_routing_b200 import whisper_train as wt
+    from speech_adapter_routing_b200.dist import FlatGradBucket
+
+    mods = [sar.RoutedLoRALinear(nn.Linear(128, 128), "default", r=16, lora_alpha=32) for _ in range(2)]
+    ws = wt._lora_params(mods)
+    assert [tuple(w.shape) for w in ws] == [(16, 128), (128, 16), (16, 128), (128, 16)]
+    h = torch.zeros(1, 4, 128)
+    assert wt._fn_inputs(ws, mods, h, False) is ws                    # no bucket: autograd accumulates
+    bucket = FlatGradBucket(ws)
+    assert wt._all_direct(mods, h.device)
+    anchor = wt._fn_inputs(ws, mods, h, False)
+    assert len(anchor) == 1 and anchor[0].numel() == 1 and anchor[0].requires_grad
+    assert wt._fn_inputs(ws, mods, h.clone().requires_grad_(True), False) == []
+    assert wt._fn_inputs(ws, mods, h, True) == []
+    ws[0].grad = None                                                  # optimizer.zero_grad(set_to_none=True) after zero_()
+    assert wt._fn_inputs(ws, mods, h, False) is ws
+    bucket.attach()
+    mods[1].add_adapter("second", 16, 32)                              # two adapters: K3's partials are scaled per adapter
+    assert not wt._all_direct(mods, h.device)
+
+    class Ctx:
+        n_ws = 4
+    assert wt._weight_grads(Ctx, [None, 1, None, 2]) == [None, 1, None, 2]
+    Ctx.n_ws = 1
+    assert wt._weight_grads(Ctx, [None] * 4) == [None]
+    with pytest.raises(RuntimeError, match="left the flat bucket"):
+        wt._weight_grads(Ctx, [None, torch.zeros(1), None, None])
