@@ -260,6 +260,10 @@ int sar_dense_fwd(const void* x, int64_t ldx, int64_t x_batch_stride, const void
  */
 int sar_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, int64_t M, int d, float eps,
                       void* stream);
+/* The same, also writing the row statistics (fp32 mean[M] and rstd[M] = 1/sqrt(var + eps)) that a LayerNorm backward
+ * needs: the training layers' forward (autograd through nn.LayerNorm in src/training/trainer.py:251-256). */
+int sar_layernorm_fwd_stats(const void* x, const void* gamma, const void* beta, void* y, float* mean, float* rstd, int64_t M,
+                            int d, float eps, void* stream);
 
 /*
  * LayerNorm fused with the LoRA down-projection of the attention projections that consume it (one pass over h):

@@ -42,6 +42,7 @@ _SIGNATURES = {
     "sar_decode_cross_attn": (c_int, [c_void_p] * 4 + [c_int] * 4 + [c_void_p]),
     "sar_logmel_fwd": (c_int, [c_void_p] * 8 + [c_int] * 4 + [c_void_p]),
     "sar_layernorm_fwd": (c_int, [c_void_p] * 4 + [c_int64, c_int, c_float, c_void_p]),
+    "sar_layernorm_fwd_stats": (c_int, [c_void_p] * 6 + [c_int64, c_int, c_float, c_void_p]),
     "sar_layernorm_lora_u_fwd": (c_int, [c_void_p] * 7 + [c_int] * 6 + [c_float, c_float, c_void_p]),
     "sar_layernorm_lora_u_supported": (c_int, [c_int] * 3),
     "sar_operand_refresh": (c_int, [c_void_p, c_int, c_int, c_void_p]),

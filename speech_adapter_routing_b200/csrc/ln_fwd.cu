@@ -21,6 +21,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 template <int NV>   // NV = ceil(d / 256) vectors per lane
 __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const uint4* __restrict__ x, const uint4* __restrict__ gamma,
                                                                const uint4* __restrict__ beta, uint4* __restrict__ y,
+                                                               float* __restrict__ mean_out, float* __restrict__ rstd_out,
                                                                long long M, int nvec, float inv_d, float eps) {
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * LN_WARPS + (threadIdx.x >> 5);
@@ -54,6 +55,10 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const uint4* __re
     }
   }
   const float rstd = rsqrtf(warp_sum(ss) * inv_d + eps);
+  if (mean_out != nullptr && lane == 0) {   // training: the statistics ATen's LayerNorm backward consumes
+    mean_out[row] = mean;
+    rstd_out[row] = rstd;
+  }
   uint4* yr = y + row * nvec;
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
@@ -76,9 +81,10 @@ __global__ void __launch_bounds__(LN_WARPS * 32) ln_fwd_kernel(const uint4* __re
   }
 }
 
-int layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, int64_t M, int d, float eps,
-                  cudaStream_t stream) {
+int layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean_out, float* rstd_out, int64_t M,
+                  int d, float eps, cudaStream_t stream) {
   if (!x || !gamma || !beta || !y) return fail(SAR_EINVAL, "layernorm: null pointer");
+  if ((mean_out == nullptr) != (rstd_out == nullptr)) return fail(SAR_EINVAL, "layernorm: mean and rstd come together");
   if (M <= 0) return fail(SAR_EINVAL, "layernorm: M must be positive");
   if (d <= 0 || d % 8 || d > LN_MAXV * 256) return fail(SAR_EINVAL, "layernorm: d must be a multiple of 8 and <= 2048");
   if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(gamma) |
@@ -95,7 +101,7 @@ int layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, i
   uint4* yp = static_cast<uint4*>(y);
   const float inv_d = 1.0f / static_cast<float>(d);
 #define SAR_LN_CASE(NV) \
-  case NV: ln_fwd_kernel<NV><<<grid, LN_WARPS * 32, 0, stream>>>(xp, gp, bp, yp, M, nvec, inv_d, eps); break;
+  case NV: ln_fwd_kernel<NV><<<grid, LN_WARPS * 32, 0, stream>>>(xp, gp, bp, yp, mean_out, rstd_out, M, nvec, inv_d, eps); break;
   switch (nv) {
     SAR_LN_CASE(1) SAR_LN_CASE(2) SAR_LN_CASE(3) SAR_LN_CASE(4) SAR_LN_CASE(5) SAR_LN_CASE(6) SAR_LN_CASE(7)
     SAR_LN_CASE(8)

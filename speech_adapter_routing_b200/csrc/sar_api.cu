@@ -296,7 +296,15 @@ int sar_layernorm_fwd(const void* x, const void* gamma, const void* beta, void* 
                       void* stream) {
   int rc = require_sm100();
   if (rc) return rc;
-  return layernorm_fwd(x, gamma, beta, y, M, d, eps, static_cast<cudaStream_t>(stream));
+  return layernorm_fwd(x, gamma, beta, y, nullptr, nullptr, M, d, eps, static_cast<cudaStream_t>(stream));
+}
+
+int sar_layernorm_fwd_stats(const void* x, const void* gamma, const void* beta, void* y, float* mean, float* rstd, int64_t M,
+                            int d, float eps, void* stream) {
+  int rc = require_sm100();
+  if (rc) return rc;
+  if (!mean || !rstd) return fail(SAR_EINVAL, "layernorm_stats: null mean / rstd");
+  return layernorm_fwd(x, gamma, beta, y, mean, rstd, M, d, eps, static_cast<cudaStream_t>(stream));
 }
 
 int sar_layernorm_lora_u_fwd(const void* h, const void* gamma, const void* beta, void* x, const void* A_cat,

@@ -87,8 +87,8 @@ int decode_cross_attn(const void* q, const void* k, const void* v, void* out, in
 int logmel_fwd(const float* wave, const float* window, const float* cos_t, const float* sin_t, const float* filters,
                float* raw_ws, int* clip_max_ws, void* out, int B, int n_samples, int n_mels, int out_bf16,
                cudaStream_t stream);
-int layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, int64_t M, int d, float eps,
-                  cudaStream_t stream);
+int layernorm_fwd(const void* x, const void* gamma, const void* beta, void* y, float* mean_out, float* rstd_out, int64_t M,
+                  int d, float eps, cudaStream_t stream);
 int ln_lora_u_fwd(const void* h, const void* gamma, const void* beta, void* x, const void* A_cat,
                   const int32_t* utt_adapter, void* u_out, int B, int T, int d, int r, int n_sets, int n_adapters,
                   float scale, float eps, cudaStream_t stream);

@@ -397,6 +397,23 @@ def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps:
     return y
 
 
+def layernorm_fwd_stats(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
+                        eps: float = 1e-5) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """LayerNorm that also returns the row statistics (sar_layernorm_fwd_stats): y bf16 like x, mean / rstd fp32
+    [..., 1] — the three results of ``torch.native_layer_norm``, for ATen's LayerNorm backward."""
+    _need_cuda(x, gamma, beta)
+    x = _bf16c(x, "x"); gamma = _bf16c(gamma, "gamma"); beta = _bf16c(beta, "beta")
+    d = x.shape[-1]
+    M = x.numel() // d
+    y = torch.empty_like(x)
+    mean = torch.empty(*x.shape[:-1], 1, dtype=torch.float32, device=x.device)
+    rstd = torch.empty_like(mean)
+    check(lib().sar_layernorm_fwd_stats(_ptr(x), _ptr(gamma), _ptr(beta), _ptr(y), _ptr(mean), _ptr(rstd), M, d, float(eps),
+                                        _stream(x)))
+    LAUNCHES["ln"] += 1
+    return y, mean, rstd
+
+
 def layernorm_lora_u_supported(d: int, r: int, n_sets: int) -> bool:
     return bool(lib().sar_layernorm_lora_u_supported(int(d), int(r), int(n_sets)))
 

@@ -405,3 +405,19 @@ def test_operand_refresh_rederives_every_block_bit_exactly(cuda_dev):
     # empty table is a no-op; a null table with entries is rejected
     _lib.check(_lib.lib().sar_operand_refresh(None, 0, 1, torch.cuda.current_stream().cuda_stream))
     assert _lib.lib().sar_operand_refresh(None, 3, 16, torch.cuda.current_stream().cuda_stream) == _lib.SAR_EINVAL
+
+
+@pytest.mark.parametrize("M,d", [(24000, 768), (37, 384), (5, 1280)])
+def test_layernorm_with_statistics_matches_aten(cuda_dev, M, d):
+    """sar_layernorm_fwd_stats: y bit-identical to sar_layernorm_fwd, mean / rstd equal to torch.native_layer_norm's
+    (fp32 two-pass on the same bf16 input) within 1e-5 relative."""
+    g = torch.Generator().manual_seed(d + M)
+    x = (torch.randn(M, d, generator=g) * 2 + 0.5).to(torch.bfloat16).to(cuda_dev)
+    w = (1 + 0.1 * torch.randn(d, generator=g)).to(torch.bfloat16).to(cuda_dev)
+    b = (0.1 * torch.randn(d, generator=g)).to(torch.bfloat16).to(cuda_dev)
+    y, mean, rstd = ops.layernorm_fwd_stats(x, w, b, 1e-5)
+    assert torch.equal(y, ops.layernorm_fwd(x, w, b, 1e-5))
+    ry, rmean, rrstd = torch.native_layer_norm(x, (d,), w, b, 1e-5)
+    assert mean.shape == rmean.shape and rstd.shape == rrstd.shape and mean.dtype == rmean.dtype == torch.float32
+    assert rel_err(mean, rmean) <= 1e-5 and rel_err(rstd, rrstd) <= 1e-5
+    assert rel_err(y, ry) <= TIGHT
