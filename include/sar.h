@@ -200,6 +200,9 @@ int sar_logmel_fwd(const float* wave, const float* window, const float* cos_tabl
 /* epilogue activations of sar_linear_fwd */
 #define SAR_ACT_NONE 0
 #define SAR_ACT_GELU 1 /* erf-form GELU, HF ACT2FN["gelu"] */
+/* sar_linear_fwd only: y = (x·Wᵀ) * GELU'(residual) — the GELU backward of the training layers fused into the dX GEMM of
+ * fc2 (autograd through ACT2FN["gelu"], $HF/modeling_whisper.py:403); `residual` carries the saved pre-activation. */
+#define SAR_ACT_GELU_BWD 2
 
 /*
  * Self-attention q‖v pair: one x, two LoRA'd projections, two row-major outputs.

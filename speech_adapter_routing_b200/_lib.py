@@ -20,7 +20,7 @@ SAR_FLAG_SAVE_U = 1
 SAR_FLAG_U_READY, SAR_FLAG_U_ONLY = 4, 8
 SAR_OP_QV_LORA_FWD, SAR_OP_ROUTER_FWD, SAR_OP_QV_LORA_BWD, SAR_OP_QV_LORA_FWD_ROWS, SAR_OP_ATTN_PROJ_FWD = 0, 1, 2, 3, 4
 SAR_RPAD = 64
-SAR_ACT_NONE, SAR_ACT_GELU = 0, 1
+SAR_ACT_NONE, SAR_ACT_GELU, SAR_ACT_GELU_BWD = 0, 1, 2
 SAR_DTYPE_F32, SAR_DTYPE_BF16 = 0, 1
 
 # name -> (restype, argtypes); mirrors include/sar.h one to one

@@ -64,7 +64,7 @@ struct K1V2Params {
   int u_w_ld, u_w_group;
 };
 
-enum : int { EPI_RES = 1, EPI_GELU = 2, EPI_SCALE = 4 };
+enum : int { EPI_RES = 1, EPI_GELU = 2, EPI_SCALE = 4, EPI_DGELU = 8 };   // DGELU: y = acc * GELU'(residual operand)
 // Epilogue warps per CTA.  The GELU epilogue is latency-bound with one warp per SMSP (ncu: 31 % wait + 12 % MUFU
 // scoreboard stalls) and the residual epilogue waits on its global loads: two warps per TMEM lane quadrant interleave
 // their dependency chains, and each then owns at most two column chunks whose residual rows are both requested before
@@ -526,7 +526,9 @@ k1v2_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CU
                                 make_float2(__uint_as_float(bw[i] << 16), __uint_as_float(bw[i] & 0xFFFF0000u)));
               if constexpr ((EPI & EPI_GELU) != 0) av = gelu_erf2(av);
               if constexpr ((EPI & EPI_SCALE) != 0) av = fmul2(av, make_float2(oscale, oscale));
-              if constexpr ((EPI & EPI_RES) != 0)
+              if constexpr ((EPI & EPI_DGELU) != 0)   // GELU backward: the "residual" operand is the pre-activation
+                av = fmul2(av, gelu_grad2(make_float2(__uint_as_float(rw[i] << 16), __uint_as_float(rw[i] & 0xFFFF0000u))));
+              else if constexpr ((EPI & EPI_RES) != 0)
                 av = fadd2(av, make_float2(__uint_as_float(rw[i] << 16), __uint_as_float(rw[i] & 0xFFFF0000u)));
               const float a0 = av.x, a1 = av.y;
               pk[i] = pack_bf16x2(a0, a1);
@@ -724,6 +726,9 @@ static int k1v2_dispatch_epi(const K1Args& a, int epi, cudaStream_t stream) {
     case EPI_GELU | EPI_RES:
       if constexpr (!LORA) return k1v2_launch<BLOCK_N, false, EPI_GELU | EPI_RES, 8>(a, stream);
       break;
+    case EPI_DGELU | EPI_RES:
+      if constexpr (!LORA) return k1v2_launch<BLOCK_N, false, EPI_DGELU | EPI_RES, 8>(a, stream);
+      break;
     default: break;
   }
   return fail(SAR_EINVAL, "k1v2: unsupported epilogue combination (residual / GELU are dense-only)");
@@ -735,6 +740,10 @@ int k1v2_qv_lora_fwd(const K1Args& a, int block_n, cudaStream_t stream) {
   int epi = 0;
   if (a.residual) epi |= EPI_RES;
   if (a.act == SAR_ACT_GELU) epi |= EPI_GELU;
+  if (a.act == SAR_ACT_GELU_BWD) {
+    if (!a.residual) return fail(SAR_EINVAL, "k1v2: SAR_ACT_GELU_BWD reads the pre-activation through the residual operand");
+    epi |= EPI_DGELU;
+  }
   if (a.n_seg > 0)
     for (int s = 0; s < n_seg; ++s)
       if (a.seg_scale[s] != 1.0f) epi |= EPI_SCALE;
@@ -817,7 +826,7 @@ int attn_proj_fwd(const K1Args& a, cudaStream_t stream) {
   if (al & 15) return fail(SAR_EINVAL, "attn_proj: pointers must be 16-byte aligned");
   // <= 128 rows, dense, row-major: weight-streaming problem -> narrow single-CTA tiles on every SM (skinny_fwd.cu)
   if (a.B == 1 && !a.block_n_override && !a.grid_override && !a.x_batch_stride && !a.y_batch_stride &&
-      skinny_applicable(a, a.T))
+      a.act != SAR_ACT_GELU_BWD && skinny_applicable(a, a.T))
     return skinny_fwd(a, a.T, stream);
   int bn = a.block_n_override;
   if (!bn) {

@@ -222,7 +222,8 @@ int sar_linear_fwd(const void* x, int x_head_major, const void* W, const void* b
                    int B, int T, int d_in, int d_out, int act, uint32_t flags, void* stream) {
   int rc = require_sm100();
   if (rc) return rc;
-  if (act != SAR_ACT_NONE && act != SAR_ACT_GELU) return fail(SAR_EINVAL, "sar_linear_fwd: unknown activation");
+  if (act != SAR_ACT_NONE && act != SAR_ACT_GELU && act != SAR_ACT_GELU_BWD)
+    return fail(SAR_EINVAL, "sar_linear_fwd: unknown activation");
   if (reinterpret_cast<uintptr_t>(residual) & 15) return fail(SAR_EINVAL, "sar_linear_fwd: residual must be 16-byte aligned");
   K1Args a{};
   a.x = x; a.W = W; a.bias = bias; a.B = B; a.T = T; a.d_in = d_in; a.d_out = d_out; a.r = 16; a.scale = 0.f;

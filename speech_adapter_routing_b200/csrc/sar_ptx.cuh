@@ -347,6 +347,30 @@ __device__ __forceinline__ float2 gelu_erf2(float2 v) {
   return fmul2(v, r);
 }
 
+// d/dx GELU(x) = Phi(x) + x * phi(x) for two elements: Phi from the same fitted logistic form as gelu_erf2 (so forward and
+// backward agree), phi(x) = exp(-x^2 / 2) / sqrt(2 pi) on MUFU.EX2.  Used by the GELU-backward epilogue (training).
+__device__ __forceinline__ float2 gelu_grad2(float2 v) {
+  constexpr float K = -2.0f * 1.4426950408889634f;
+  float2 v2 = fmul2(v, v);
+  v2.x = fminf(v2.x, 100.0f);
+  v2.y = fminf(v2.y, 100.0f);
+  float2 p = ffma2(v2, make_float2(K * -0.0003515167885699055f, K * -0.0003515167885699055f),
+                   make_float2(K * 0.037005646022542554f, K * 0.037005646022542554f));
+  p = ffma2(p, v2, make_float2(K * 0.7975078842850871f, K * 0.7975078842850871f));
+  const float2 x = fmul2(v, p);
+  float2 e, r, g;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.x) : "f"(x.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e.y) : "f"(x.y));
+  const float2 d = fadd2(e, make_float2(1.0f, 1.0f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.x) : "f"(d.x));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r.y) : "f"(d.y));
+  const float2 h = fmul2(v2, make_float2(-0.5f * 1.4426950408889634f, -0.5f * 1.4426950408889634f));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(g.x) : "f"(h.x));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(g.y) : "f"(h.y));
+  // Phi + x * phi
+  return ffma2(fmul2(v, make_float2(0.3989422804014327f, 0.3989422804014327f)), g, r);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);  // .x = lo (low 16 bits), .y = hi
   return *reinterpret_cast<uint32_t*>(&h);

@@ -22,7 +22,7 @@ import torch
 import torch.nn.functional as F
 
 from . import ops
-from ._lib import SAR_ACT_NONE
+from ._lib import SAR_ACT_GELU_BWD, SAR_ACT_NONE
 from .lora_linear import RoutedLoRALinear, _notify_grad_ready
 from .routing import current_mix_weights
 
@@ -30,6 +30,7 @@ ENABLED = __import__("os").environ.get("SAR_FUSED_TRAIN", "1") != "0"
 # softmax(QKᵀ)V forward / backward: "cudnn" or "flash" — ATen's fused-attention ops, called directly (no nested autograd
 # graph: one host call each way, CUDA-graph capturable, and every saved tensor can go through ctx.save_for_backward).
 SDPA_IMPL = __import__("os").environ.get("SAR_TRAIN_SDPA", "cudnn")
+FUSED_GELU_BWD = __import__("os").environ.get("SAR_TRAIN_FUSED_GELU_BWD", "1") != "0"   # A/B switch
 OWN_LN = __import__("os").environ.get("SAR_TRAIN_OWN_LN", "1") != "0"      # A/B switch: LayerNorm forward on sar_layernorm_fwd_stats
 # Set by train_graph.GraphedTrainStep around its calls: under CUDA-graph capture HF materialises the decoder's causal mask
 # as a tensor instead of passing None (transformers/masking_utils.py:262-275 refuses to skip it while "tracing"); the
@@ -292,8 +293,11 @@ def _ffn_fwd(layer, pk, h: torch.Tensor):
 def _ffn_bwd(layer, pk, saved, dout: torch.Tensor) -> torch.Tensor:
     h, mean3, rstd3, pre = saved
     B, T, d = h.shape
-    df = ops.linear_fwd(dout.reshape(1, B * T, d), _wt(pk["fc2"]), None)                   # [1, M, ffn]
-    dpre = torch.ops.aten.gelu_backward(df, pre)
+    if FUSED_GELU_BWD:      # dpre = (dout·W2) * GELU'(pre) in the dX GEMM's epilogue (pre rides in as the residual operand)
+        dpre = ops.linear_fwd(dout.reshape(1, B * T, d), _wt(pk["fc2"]), None, residual=pre, act=SAR_ACT_GELU_BWD)
+    else:
+        df = ops.linear_fwd(dout.reshape(1, B * T, d), _wt(pk["fc2"]), None)               # [1, M, ffn]
+        dpre = torch.ops.aten.gelu_backward(df, pre)
     dx3 = ops.linear_fwd(dpre, _wt(pk["fc1"]), None).view(B, T, d)
     return dout + _ln_bwd(dx3, h, mean3, rstd3, layer.final_layer_norm)
 

@@ -405,3 +405,23 @@ def test_attn_fwd_matches_fp32_softmax(cuda_dev, B, H, Tq, Tk, causal):
     # a (b, h) pair computed alone gives identical bits (tiles never cross heads)
     one = ops.attn_fwd(q[:1, :1].contiguous(), k[:1, :1].contiguous(), v[:1, :1].contiguous(), causal)
     assert torch.equal(one[0, 0], out[0, 0])
+
+
+@pytest.mark.parametrize("M,d_in,d_out", [(24000, 768, 3072), (300, 384, 1536), (130, 128, 256)])
+def test_linear_with_gelu_backward_epilogue(cuda_dev, M, d_in, d_out):
+    """SAR_ACT_GELU_BWD: y = (x·Wᵀ) * GELU'(pre) — the dX GEMM of fc2 with the GELU backward in its epilogue — against
+    torch's erf-form gelu_backward on the fp32 product (one bf16 rounding of the result: 2^-7 of the largest value)."""
+    from speech_adapter_routing_b200._lib import SAR_ACT_GELU_BWD
+
+    g = torch.Generator().manual_seed(M + d_out)
+    x = (torch.randn(1, M, d_in, generator=g) * 0.5).to(torch.bfloat16).to(cuda_dev)
+    W = (torch.randn(d_out, d_in, generator=g) * 0.05).to(torch.bfloat16).to(cuda_dev)
+    pre = (torch.randn(1, M, d_out, generator=g) * 1.5).to(torch.bfloat16).to(cuda_dev)
+    y = ops.linear_fwd(x, W, None, residual=pre, act=SAR_ACT_GELU_BWD)
+    ref = torch.ops.aten.gelu_backward(x.float() @ W.float().t(), pre.float())
+    assert rel_err(y, ref) <= TIGHT
+    # far tails: GELU' -> 0 / 1 without NaNs
+    pre2 = torch.full_like(pre, 30.0); pre2[..., ::2] = -30.0
+    y2 = ops.linear_fwd(x, W, None, residual=pre2, act=SAR_ACT_GELU_BWD)
+    ref2 = torch.ops.aten.gelu_backward(x.float() @ W.float().t(), pre2.float())
+    assert torch.isfinite(y2.float()).all() and rel_err(y2, ref2) <= TIGHT
