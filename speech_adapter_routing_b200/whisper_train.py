@@ -5,14 +5,16 @@ gradient checkpointing on by default, src/models/whisper_lora.py:81-83): ~45 lau
 autograd backward.  Only the LoRA tensors train; the base weights are frozen, so the backward needs exactly
 
     dX through every dense layer                      -> the tcgen05 pair kernel on the transposed weight (sar_linear_fwd)
+    GELU backward                                     -> the epilogue of fc2's dX GEMM (SAR_ACT_GELU_BWD)
     dX, dA, dB at q_proj / v_proj                     -> K3 (sar_qv_lora_bwd), accumulating into the flat gradient bucket
-    LayerNorm, GELU, softmax(QKᵀ)V backward           -> ATen / SDPA kernels (library) on the tensors the forward saved
+    LayerNorm, softmax(QKᵀ)V backward                 -> ATen kernels (library) on the tensors the forward saved
 
-Each layer is ONE ``torch.autograd.Function``: its forward runs the same fused launches as inference (LayerNorm statistics
-come from ATen's LayerNorm so that its backward can reuse them) and saves the handful of tensors the backward needs; under
-HF's gradient checkpointing that forward is the recompute and the saved tensors live only until the layer's backward.
-The HF modules, their parameters and their attribute paths are untouched; when a precondition fails (dropout active,
-masks, KV cache, non-bf16, LoRA on other modules) the layer keeps HF's body over the K1 / K3 module slots.
+Each layer is ONE ``torch.autograd.Function``: its forward runs the fused launches of inference (row-major projection
+outputs viewed as heads, LayerNorm on the own kernel with its statistics written out for ATen's LayerNorm backward) and
+hands every tensor the backward needs to ``ctx.save_for_backward`` — so HF's gradient checkpointing really drops and
+recomputes them.  The HF modules, their parameters and their attribute paths are untouched; when a precondition fails
+(dropout active, masks, KV cache, non-bf16, LoRA on other modules) the layer keeps HF's body over the K1 / K3 module
+slots (``REFUSED`` says why).
 """
 from __future__ import annotations
 
