@@ -541,6 +541,10 @@ def _lm_head_forward(self, x: torch.Tensor) -> torch.Tensor:
     """proj_out (:1135): [.., d] x [V, d]ᵀ on the pair kernel.  V = 51865 / 51866 is not a multiple of 8, so the logits
     live in a buffer whose row stride is padded to 8 elements and the returned tensor is the [.., :V] view of it."""
     W = self.weight
+    if x.dtype == torch.float32 and torch.is_grad_enabled() and W.dtype == torch.bfloat16:
+        from . import whisper_train
+
+        x = whisper_train.autocast_to_bf16(x)   # fp32 out of HF's final LayerNorm under autocast(bf16): F.linear's own cast
     if not (FUSED_BLOCKS_ENABLED and x.is_cuda and x.dtype == torch.bfloat16 and W.dtype == torch.bfloat16
             and self.bias is None and W.is_contiguous() and x.shape[-1] % 8 == 0):
         return self._sar_hf_forward(x)

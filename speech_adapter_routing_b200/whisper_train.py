@@ -329,9 +329,21 @@ def _fn_inputs(ws: List[torch.Tensor], mods: List[RoutedLoRALinear], h: torch.Te
     return [torch.zeros((), dtype=torch.float32, device=h.device, requires_grad=True)]
 
 
+def _no_autocast():
+    """The reference trainer runs its forward under ``torch.autocast(bf16)`` (src/training/trainer.py:328-331).  Everything
+    inside the layer Functions is already bf16 with explicit fp32 statistics; autocast would only re-route the few ATen
+    calls (LayerNorm fallback -> fp32 outputs) — so it is switched off for their bodies."""
+    return torch.autocast(device_type="cuda", enabled=False)
+
+
 class _EncoderLayerFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, h, layer, idx, *lora_ws):
+        with _no_autocast():
+            return _EncoderLayerFn._forward(ctx, h, layer, idx, *lora_ws)
+
+    @staticmethod
+    def _forward(ctx, h, layer, idx, *lora_ws):
         pk = layer._sar_pack
         h = h.contiguous()
         H = layer.self_attn.num_heads
@@ -358,6 +370,11 @@ class _EncoderLayerFn(torch.autograd.Function):
 class _DecoderLayerFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, h, enc, layer, idx, *lora_ws):
+        with _no_autocast():
+            return _DecoderLayerFn._forward(ctx, h, enc, layer, idx, *lora_ws)
+
+    @staticmethod
+    def _forward(ctx, h, enc, layer, idx, *lora_ws):
         pk = layer._sar_pack
         h = h.contiguous()
         enc = enc.contiguous()
@@ -485,9 +502,27 @@ def encoder_layer_train(layer, hidden_states: torch.Tensor, kwargs) -> Optional[
     return _EncoderLayerFn.apply(hidden_states, layer, idx, *_fn_inputs(ws, qkv.lora_mods, hidden_states, False))
 
 
+_ENC_CAST: List = [None, None]        # (weakref to the fp32 encoder output, its bf16 cast): one cast per step, not per layer
+
+
+def autocast_to_bf16(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    """Under ``torch.autocast(bf16)`` (the reference trainer's forward, src/training/trainer.py:328-331) HF's LayerNorms
+    return fp32, and the next projection would cast that input to bf16 anyway: do that cast here, once, so the fused
+    layers see what their kernels take.  Anything else is returned unchanged."""
+    if (t is None or t.dtype != torch.float32 or not t.is_cuda or not torch.is_autocast_enabled("cuda")
+            or torch.get_autocast_dtype("cuda") != torch.bfloat16):
+        return t
+    import weakref
+
+    src = _ENC_CAST[0]() if _ENC_CAST[0] is not None else None
+    if src is not t:
+        _ENC_CAST[0], _ENC_CAST[1] = weakref.ref(t), t.to(torch.bfloat16)
+    return _ENC_CAST[1]
+
+
 def decoder_layer_train(layer, hidden_states: torch.Tensor, encoder_hidden_states: Optional[torch.Tensor],
                         kwargs) -> Optional[torch.Tensor]:
-    e = encoder_hidden_states
+    e = autocast_to_bf16(encoder_hidden_states)
     if e is None:
         why = "no encoder states"
     elif not (e.is_cuda and e.dtype == torch.bfloat16):

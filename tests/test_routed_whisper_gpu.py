@@ -759,3 +759,48 @@ def test_eager_training_loop_refreshes_operands_in_one_launch_and_stays_exact(cu
     assert loss_a == loss_b
     for a, b in zip(ga, gb):
         assert rel_err(a, b) <= 5e-3
+
+
+def test_training_step_under_autocast_as_the_reference_trainer_runs_it(cuda_dev, monkeypatch):
+    """src/training/trainer.py:328-331 wraps the forward in torch.autocast(bf16) and backpropagates loss / accumulation
+    steps: the fused training layers (and the LM head Function) take that unchanged — same layers taken, gradients equal
+    to the plain call's scaled by 1 / 2 (cuDNN's atomically accumulated dQ aside)."""
+    monkeypatch.setenv("SAR_RANDOM_INIT", "1")
+    from speech_adapter_routing_b200 import whisper_train
+
+    dev = cuda_dev
+    torch.manual_seed(7)
+    w = sar.WhisperLoRA("whisper-tiny", lora_r=16, lora_alpha=32, lora_dropout=0.0, device="cuda",
+                        use_gradient_checkpointing=True)
+    w.train()
+    cfg = w.model.config
+    g = torch.Generator().manual_seed(3)
+    with torch.no_grad():
+        for m in sar.lora_modules(w.model).values():
+            m.lora_B["default"].weight.copy_((torch.randn(m.out_features, 16, generator=g) * 0.02).to(dev))
+    x = owhisper.make_input_features(2, cfg.num_mel_bins, [0, 0], 1, seed=8).to(dev).to(torch.bfloat16)
+    _, labels = owhisper.make_decoder_inputs(2, 6, cfg.vocab_size, cfg.decoder_start_token_id)
+    labels = labels.to(dev)
+
+    def grads(autocast):
+        for p in w.model.parameters():
+            p.grad = None
+        calls0 = dict(whisper_train.CALLS)
+        if autocast:
+            with torch.autocast(device_type="cuda", dtype=torch.bfloat16):
+                loss = w(input_features=x, labels=labels).loss
+            (loss / 2).backward()
+        else:
+            loss = w(input_features=x, labels=labels).loss
+            loss.backward()
+        taken = {k: whisper_train.CALLS.get(k, 0) - calls0.get(k, 0) for k in ("encoder_layers", "decoder_layers", "lm_head")}
+        return loss.item(), {n: p.grad.float().clone() for n, p in w.model.named_parameters() if p.grad is not None}, taken
+
+    loss_a, ga, taken_a = grads(False)
+    loss_b, gb, taken_b = grads(True)
+    assert taken_a == taken_b and taken_b["decoder_layers"] >= cfg.decoder_layers and taken_b["lm_head"] >= 1, (
+        taken_a, taken_b, whisper_train.REFUSED)
+    assert abs(loss_a - loss_b) <= 1e-2 * abs(loss_a)
+    assert len(ga) == len(gb) == 2 * 6 * cfg.encoder_layers
+    for n, a in ga.items():
+        assert rel_err(2 * gb[n], a) <= 1e-2, n
