@@ -248,12 +248,29 @@ def _is_gelu(layer: nn.Module) -> bool:
 
 
 def _dropout_active(layer: nn.Module) -> bool:
-    """True when HF's body would apply dropout (training mode with a non-zero rate): the fused bodies have none."""
+    """True when HF's body (or PEFT's LoRA branch) would apply dropout: the fused inference bodies have none."""
+    return _layer_dropout_active(layer) or _lora_dropout_active(layer)
+
+
+def _layer_dropout_active(layer: nn.Module) -> bool:
+    """Whisper's own dropouts (hidden, activation, attention) in training mode with a non-zero rate."""
     if not layer.training:
         return False
     attn_p = max(float(getattr(layer.self_attn, "dropout", 0.0)),
                  float(getattr(getattr(layer, "encoder_attn", None), "dropout", 0.0) or 0.0))
     return max(float(layer.dropout), float(layer.activation_dropout), attn_p) > 0.0
+
+
+def _lora_dropout_active(layer: nn.Module) -> bool:
+    """lora_dropout > 0 on a LoRA'd projection of this layer, in training mode (the inference bodies apply none)."""
+    for attn in (layer.self_attn, getattr(layer, "encoder_attn", None)):
+        if attn is None:
+            continue
+        for name in ("q_proj", "k_proj", "v_proj"):
+            m = getattr(attn, name, None)
+            if isinstance(m, RoutedLoRALinear) and m.training and m._dropout_active():
+                return True
+    return False
 
 
 def _fast_path_ok(layer: nn.Module, h: torch.Tensor, kwargs) -> bool:

@@ -155,7 +155,7 @@ def _lora_bwd(m: RoutedLoRALinear, dy: torch.Tensor, x: torch.Tensor, u: torch.T
 # Tensors one attention keeps for its backward, in save order.  They all travel through ctx.save_for_backward, so under
 # HF's gradient checkpointing (non-reentrant: the first forward runs with grad enabled) the saved-tensor hooks really drop
 # them and the recompute really refills them — Python attributes on ctx would keep every activation alive.
-_ATTN_FIELDS = ("x_q", "x_kv", "u_q", "u_kv", "q", "k", "v", "o", "lse", "cq", "ck", "seed", "off")
+_ATTN_FIELDS = ("x_q", "x_kv", "u_q", "u_kv", "q", "k", "v", "o", "lse", "cq", "ck", "seed", "off", "g_q", "g_kv")
 _N_ATTN = len(_ATTN_FIELDS)
 
 
@@ -171,6 +171,53 @@ def _lora_u(proj, x, idx):
     if idx is None or proj.A is None:
         return None
     return ops.lora_u_fwd(x, proj.A, idx, proj.n_sets, proj.scale, proj.W.shape[0] // len(proj.mods))
+
+
+def _active_dropout(m):
+    """The nn.Dropout PEFT would apply to this module's LoRA input right now (training mode, p > 0), else None."""
+    if not (isinstance(m, RoutedLoRALinear) and m.training and m._dropout_active()):
+        return None
+    return m.lora_dropout[m.active_adapter]
+
+
+def _lora_u_dropout(proj, x, idx, u):
+    """PEFT drops the input of the LoRA branch only: y = base(x) + s·B(A(drop(x))) (src/models/whisper_lora.py:30, default
+    p = 0.1), one independent mask per module.  With g = drop(1) - 1 (-1 where dropped, p/(1-p) where kept) drop(x) =
+    x + x∘g, so U gains s·(x∘g)·Aᵀ — a [M, d] x [d, r] product per module on top of the fused U pass; everything
+    downstream (the dense launch with the low-rank K block) is unchanged.  Returns the per-set masks g stacked
+    [n_sets, B, T, d] (None when no module of the call drops)."""
+    drops = [_active_dropout(m) for m in proj.lora_mods]
+    if u is None or not any(d is not None for d in drops):
+        return None
+    B, T, d = x.shape
+    gs = torch.zeros(len(drops), B, T, d, dtype=x.dtype, device=x.device)
+    for i, (m, drop) in enumerate(zip(proj.lora_mods, drops)):
+        if drop is None:
+            continue
+        g = drop(torch.ones_like(x)) - 1
+        gs[i] = g
+        A = m._stacks()["A"][0]                                        # [r, d] bf16
+        u[i] += ((x * g).view(B * T, d) @ A.t()).view(B, T, -1) * m._stacks()["scale"]
+    return gs
+
+
+def _lora_dropout_bwd(m, dy, x, g, part, grads, idx):
+    """Backward of the extra term of ``_lora_u_dropout`` for one module (K3 already did the drop-free part, including dB,
+    which only sees U): dA += vᵀ(x∘g), dx += (v·A)∘g with v = s·dy·B."""
+    st = m._stacks(backward=True)
+    B, T, d = x.shape
+    M = B * T
+    v = (dy.reshape(M, -1) @ st["Bt"][0].t()) * st["scale"]           # [M, r]
+    dA_c = (v.t() @ (x * g).view(M, d)).float()                        # [r, d]
+    part = part + ((v @ st["A"][0]).view(B, T, d) * g)
+    direct = _direct_views(m, st, x.device)
+    if direct is not None:
+        direct[0][0].add_(dA_c)
+    else:
+        w = m.lora_A[m.adapter_order[0]].weight
+        if grads[0] is not None:
+            grads[0] = grads[0] + dA_c[: w.shape[0]].to(grads[0].dtype)
+    return part, grads
 
 
 def _sdpa_fwd(q, k, v, is_causal: bool):
@@ -203,24 +250,27 @@ def _attn_fwd(proj_q, proj_kv, out_pack, x_q, x_kv, idx, causal: bool, residual:
     out_proj + residual.  proj_q produces q (and k, v when proj_kv is None: self-attention); proj_kv the cross-attention
     k | v from ``x_kv``.  Returns (h_out, saved tensors in _ATTN_FIELDS order, meta)."""
     u_q = _lora_u(proj_q, x_q, idx)
+    g_q = _lora_u_dropout(proj_q, x_q, idx, u_q)
     ys = proj_q(x_q, idx if proj_q.lora_mods else None, u=u_q, head_major=False)
-    u_kv = None
+    u_kv = g_kv = None
     if proj_kv is None:
         q, k, v = ys
     else:
         (q,) = ys
         u_kv = _lora_u(proj_kv, x_kv, idx)
+        g_kv = _lora_u_dropout(proj_kv, x_kv, idx, u_kv)
         k, v = proj_kv(x_kv, idx if proj_kv.lora_mods else None, u=u_kv, head_major=False)
     is_causal = causal and q.shape[1] > 1
     o, extra, meta = _sdpa_fwd(_heads(q, H), _heads(k, H), _heads(v, H), is_causal)
     _trace("attn.fwd u_q,u_kv,q,k,v,o", u_q, u_kv, q, k, v, o)
     p = out_pack.get()
     out = ops.linear_fwd(_to_rows(o), p.W, p.b, residual, SAR_ACT_NONE)
-    return out, [x_q, x_kv, u_q, u_kv, q, k, v, o] + extra, (meta, is_causal, H)
+    return out, [x_q, x_kv, u_q, u_kv, q, k, v, o] + extra + [g_q, g_kv], (meta, is_causal, H)
 
 
-def _proj_bwd(proj, x, u, idx, dys: List[torch.Tensor]):
-    """dX and the LoRA gradients of one fused projection call.  ``dys``: row-major output gradients per segment."""
+def _proj_bwd(proj, x, u, idx, dys: List[torch.Tensor], gs: Optional[torch.Tensor] = None):
+    """dX and the LoRA gradients of one fused projection call.  ``dys``: row-major output gradients per segment; ``gs``:
+    the lora_dropout masks of the forward (``_lora_u_dropout``) or None."""
     dx = None
     grads: List[Optional[torch.Tensor]] = []
     set_i = 0
@@ -231,6 +281,8 @@ def _proj_bwd(proj, x, u, idx, dys: List[torch.Tensor]):
         if lora and idx is not None:
             B, T, _ = x.shape
             part, g = _lora_bwd(m, dy, x, u[set_i].reshape(B * T, -1), idx)
+            if gs is not None and _active_dropout(m) is not None:
+                part, g = _lora_dropout_bwd(m, dy, x, gs[set_i], part, g, idx)
             grads += g
             set_i += 1
         else:
@@ -249,17 +301,17 @@ def _proj_bwd(proj, x, u, idx, dys: List[torch.Tensor]):
 def _attn_bwd(proj_q, proj_kv, out_pack, idx, saved, meta, dh_out: torch.Tensor):
     """dh_out: gradient of out_proj's output (the residual branch is the caller's).  Returns (dx_q, dx_kv, LoRA grads of
     proj_q, LoRA grads of proj_kv)."""
-    x_q, x_kv, u_q, u_kv, q, k, v, o, lse, cq, ck, seed, off = saved
+    x_q, x_kv, u_q, u_kv, q, k, v, o, lse, cq, ck, seed, off, g_q, g_kv = saved
     sd_meta, is_causal, H = meta
     do = _to_heads(_dense_dx(dh_out, out_pack), H)
     dq, dk, dv = _sdpa_bwd(do, _heads(q, H), _heads(k, H), _heads(v, H), o, lse, cq, ck, seed, off, sd_meta, is_causal)
     _trace("attn.bwd do,dq,dk,dv", do, dq, dk, dv)
     dq, dk, dv = _to_rows(dq), _to_rows(dk), _to_rows(dv)
     if proj_kv is None:
-        dx, g = _proj_bwd(proj_q, x_q, u_q, idx, [dq, dk, dv])
+        dx, g = _proj_bwd(proj_q, x_q, u_q, idx, [dq, dk, dv], g_q)
         return dx, None, g, []
-    dxq, gq = _proj_bwd(proj_q, x_q, u_q, idx, [dq])
-    dxkv, gkv = _proj_bwd(proj_kv, x_kv, u_kv, idx, [dk, dv])
+    dxq, gq = _proj_bwd(proj_q, x_q, u_q, idx, [dq], g_q)
+    dxkv, gkv = _proj_bwd(proj_kv, x_kv, u_kv, idx, [dk, dv], g_kv)
     return dxq, dxkv, gq, gkv
 
 
@@ -456,7 +508,7 @@ REFUSED = {"encoder": "", "decoder": ""}     # why the last layer call kept HF's
 
 
 def _train_refusal(layer, h: torch.Tensor, kwargs) -> str:
-    from .whisper_blocks import FUSED_BLOCKS_ENABLED, _dropout_active
+    from .whisper_blocks import FUSED_BLOCKS_ENABLED, _layer_dropout_active
 
     if not (ENABLED and FUSED_BLOCKS_ENABLED):
         return "switched off"
@@ -466,7 +518,7 @@ def _train_refusal(layer, h: torch.Tensor, kwargs) -> str:
         return f"hidden states {tuple(h.shape)} {h.dtype} {h.device.type}"
     if kwargs.get("output_attentions", False):
         return "output_attentions"
-    if _dropout_active(layer):
+    if _layer_dropout_active(layer):          # Whisper's own dropouts; lora_dropout is handled (_lora_u_dropout)
         return "dropout active"
     return ""
 
@@ -476,9 +528,9 @@ def _packs_refusal(*projs) -> str:
         if not p.ok:
             return "projection pack unsupported"
         for m in p.lora_mods:
-            if m.training and m._dropout_active():       # lora_dropout > 0: the module slot's correction term applies
-                return "lora_dropout active"
             r = next(iter(m.r.values()))
+            if m.training and m._dropout_active() and (len(m.adapter_order) != 1 or r % 16):
+                return "lora_dropout with several adapters / a padded rank"   # the module slot's correction term applies
             if r % 16 or r > 64:
                 return f"rank {r}"
     return ""

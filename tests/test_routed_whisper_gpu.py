@@ -804,3 +804,66 @@ def test_training_step_under_autocast_as_the_reference_trainer_runs_it(cuda_dev,
     assert len(ga) == len(gb) == 2 * 6 * cfg.encoder_layers
     for n, a in ga.items():
         assert rel_err(2 * gb[n], a) <= 1e-2, n
+
+
+class _FixedMaskDropout(torch.nn.Dropout):
+    """nn.Dropout whose mask depends only on (seed, shape): the fused layers and HF's bodies draw it in different orders."""
+
+    def __init__(self, p, seed):
+        super().__init__(p)
+        self.seed = seed
+
+    def forward(self, x):
+        if not self.training or self.p == 0:
+            return x
+        g = torch.Generator().manual_seed(self.seed)
+        keep = (torch.rand(x.shape, generator=g) >= self.p).to(x.device)
+        return x * keep.to(x.dtype) / (1 - self.p)
+
+
+def test_fused_training_layers_with_lora_dropout_equal_hf_bodies_with_the_same_masks(cuda_dev, monkeypatch):
+    """The reference's default lora_dropout = 0.1 (src/models/whisper_lora.py:30): PEFT drops the LoRA branch's input only.
+    The fused training layers add s·(x∘g)·Aᵀ to U (whisper_train._lora_u_dropout) and the matching dA / dx terms; HF's
+    bodies over the K1 / K3 module slots add the same remainder with autograd ops (checked against PEFT's formula in
+    test_training_forward_backward_with_lora_dropout_matches_pefts_formula).  With identical masks both give the same
+    loss and gradients."""
+    monkeypatch.setenv("SAR_RANDOM_INIT", "1")
+    from speech_adapter_routing_b200 import whisper_train
+
+    dev = cuda_dev
+    torch.manual_seed(13)
+    w = sar.WhisperLoRA("whisper-tiny", lora_r=16, lora_alpha=32, lora_dropout=0.1, device="cuda",
+                        use_gradient_checkpointing=False)
+    w.train()
+    cfg = w.model.config
+    g = torch.Generator().manual_seed(3)
+    with torch.no_grad():
+        for i, m in enumerate(sar.lora_modules(w.model).values()):
+            m.lora_B["default"].weight.copy_((torch.randn(m.out_features, 16, generator=g) * 0.02).to(dev))
+            m.lora_dropout["default"] = _FixedMaskDropout(0.3, 1000 + i)      # a rate that matters
+    w.train()
+    x = owhisper.make_input_features(2, cfg.num_mel_bins, [0, 0], 1, seed=8).to(dev).to(torch.bfloat16)
+    _, labels = owhisper.make_decoder_inputs(2, 6, cfg.vocab_size, cfg.decoder_start_token_id)
+    labels = labels.to(dev)
+
+    def grads(fused):
+        for p in w.model.parameters():
+            p.grad = None
+        monkeypatch.setattr(whisper_train, "ENABLED", fused)
+        calls0 = dict(whisper_train.CALLS)
+        loss = w(input_features=x, labels=labels).loss
+        loss.backward()
+        taken = whisper_train.CALLS["decoder_layers"] - calls0["decoder_layers"]
+        return loss.item(), {n: p.grad.float().clone() for n, p in w.model.named_parameters() if p.grad is not None}, taken
+
+    loss_f, gf, taken_f = grads(True)
+    loss_h, gh, taken_h = grads(False)
+    assert taken_f == cfg.decoder_layers and taken_h == 0, whisper_train.REFUSED
+    assert abs(loss_f - loss_h) <= 1e-2 * abs(loss_h)
+    for n, a in gh.items():
+        assert rel_err(gf[n], a) <= 1.2e-1, n
+    # and the masks do matter: without dropout the gradients are different
+    for m in sar.lora_modules(w.model).values():
+        m.lora_dropout["default"].p = 0.0
+    _, g0, _ = grads(True)
+    assert max(rel_err(g0[n], gf[n]) for n in gf) > 2e-1
