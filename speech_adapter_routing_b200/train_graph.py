@@ -46,6 +46,8 @@ class GraphedTrainStep:
         self.loss: Optional[torch.Tensor] = None
         dev = input_features.device
         self.refresh: Optional[OperandRefresh] = None
+        if check and any(isinstance(m, torch.nn.Dropout) and m.p > 0 and m.training for m in model.modules()):
+            check = False       # an eager step and a replay draw different dropout masks: nothing to compare bit-wise
         reference = self._eager_reference() if check else None
         failure: Optional[BaseException] = None
         try:

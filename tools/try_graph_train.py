@@ -5,7 +5,7 @@ import torch
 import speech_adapter_routing_b200 as sar
 dev = torch.device("cuda")
 for ckpt in ((False,) if len(sys.argv) < 2 else (True,)):
-    w = sar.WhisperLoRA("whisper-small", lora_r=16, lora_alpha=32, lora_dropout=0.0, device="cuda", use_gradient_checkpointing=ckpt)
+    w = sar.WhisperLoRA("whisper-small", lora_r=16, lora_alpha=32, lora_dropout=float(os.environ.get("DROPOUT", "0")), device="cuda", use_gradient_checkpointing=ckpt)
     w.train()
     cfg = w.model.config
     params = [p for p in w.model.parameters() if p.requires_grad]
