@@ -1,3 +1,6 @@
+"""Eager vs captured training step (whisper-small r16, 16 clips): timing and gradient agreement.  argv[1] = "ckpt" turns gradient
+checkpointing on; env: DROPOUT=p (lora_dropout), OPT=1 (AdamW + clip inside the eager loop), OVERLAP=1 (chunked all-reduce
+hooks), SAR_TRAIN_SDPA=cudnn|flash, SAR_TRAIN_OWN_LN=0, SAR_TRAIN_FUSED_GELU_BWD=0 (A/B switches of whisper_train.py)."""
 import os, sys, time
 sys.path.insert(0, "/root/repo")
 os.environ.setdefault("SAR_RANDOM_INIT", "1")
