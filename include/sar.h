@@ -27,7 +27,7 @@ extern "C" {
 #endif
 
 #define SAR_VERSION_MAJOR 0
-#define SAR_VERSION_MINOR 1
+#define SAR_VERSION_MINOR 2 /* 0.2: + layernorm_lora_u, layernorm_fwd_stats, router_fwd_fused_ln, attn_proj_fwd_mix, operand_refresh, SAR_ACT_GELU_BWD */
 
 /* Rank padding of the packed lora_B stack (see sar_qv_lora_fwd). */
 #define SAR_RPAD 64

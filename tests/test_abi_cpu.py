@@ -44,7 +44,7 @@ def test_library_exports_every_declared_symbol(libsar):
 
 
 def test_version_and_error_string(libsar):
-    assert libsar.sar_version() == 1
+    assert libsar.sar_version() == 2
     assert isinstance(libsar.sar_last_error(), bytes)
 
 
