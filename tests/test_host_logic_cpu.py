@@ -460,3 +460,42 @@ def test_training_layer_inputs_follow_where_the_gradients_go():
     assert wt._weight_grads(Ctx, [None] * 4) == [None]
     with pytest.raises(RuntimeError, match="left the flat bucket"):
         wt._weight_grads(Ctx, [None, torch.zeros(1), None, None])
+
+
+def test_lora_dropout_terms_of_the_fused_training_layers_complete_pefts_formula():
+    """whisper_train._lora_u_dropout / _lora_dropout_bwd (plain torch ops around the kernels): with the drop-free parts
+    that the U pass and K3 compute, they give PEFT's y = base(x) + s·B(A(drop(x))) and its gradients — checked against
+    fp32 autograd of that formula with the same mask."""
+    import types
+
+    from speech_adapter_routing_b200 import whisper_train as wt
+
+    torch.manual_seed(0)
+    d, r, s = 128, 16, 2.0
+    m = sar.RoutedLoRALinear(nn.Linear(d, d).to(torch.bfloat16), "default", r=r, lora_alpha=32, lora_dropout=0.25)
+    with torch.no_grad():
+        m.lora_B["default"].weight.normal_(0, 0.05)
+    m.train()
+    x = torch.randn(2, 5, d).to(torch.bfloat16)
+    dy = (torch.randn(2, 5, d) * 0.1).to(torch.bfloat16)
+    A16 = m.lora_A["default"].weight.detach().to(torch.bfloat16).float()
+    B16 = m.lora_B["default"].weight.detach().to(torch.bfloat16).float()
+
+    torch.manual_seed(5)                                   # the mask the module's nn.Dropout will draw
+    keep_scale = m.lora_dropout["default"](torch.ones_like(x)).float()
+    torch.manual_seed(5)
+    u = ((x.float().view(-1, d) @ A16.t()) * s).to(torch.bfloat16).view(1, 2, 5, r).clone()
+    gs = wt._lora_u_dropout(types.SimpleNamespace(lora_mods=[m]), x, None, u)
+    assert torch.equal(gs[0].float() + 1, keep_scale)
+    xr = x.float().requires_grad_(True)
+    Ar = A16.clone().requires_grad_(True)
+    u_ref = ((xr * keep_scale).view(-1, d) @ Ar.t()) * s
+    assert ((u.float().view(-1, r) - u_ref).abs().max() / u_ref.abs().max()).item() <= 2 ** -6
+    ((u_ref @ B16.t()).view(2, 5, d) * dy.float()).sum().backward()
+
+    v = (dy.float().view(-1, d) @ B16) * s                 # what K3 computes without dropout
+    dA_base, dx_base = v.t() @ x.float().view(-1, d), (v @ A16).view(2, 5, d).to(torch.bfloat16)
+    part, grads = wt._lora_dropout_bwd(m, dy, x, gs[0], dx_base, [dA_base, None], None)
+    rel = lambda a, b: ((a.float() - b.float()).abs().max() / b.float().abs().max()).item()
+    assert rel(grads[0], Ar.grad) <= 2 ** -6 and grads[1] is None
+    assert rel(part, xr.grad) <= 2 ** -6
