@@ -190,14 +190,15 @@ def _lora_u_dropout(proj, x, idx, u):
     if u is None or not any(d is not None for d in drops):
         return None
     B, T, d = x.shape
-    gs = torch.zeros(len(drops), B, T, d, dtype=x.dtype, device=x.device)
+    gs = torch.empty(len(drops), B, T, d, dtype=x.dtype, device=x.device)
+    ones = torch.ones_like(x)                                          # shared by the modules of this call (read-only)
     for i, (m, drop) in enumerate(zip(proj.lora_mods, drops)):
         if drop is None:
+            gs[i].zero_()
             continue
-        g = drop(torch.ones_like(x)) - 1
-        gs[i] = g
-        A = m._stacks()["A"][0]                                        # [r, d] bf16
-        u[i] += ((x * g).view(B * T, d) @ A.t()).view(B, T, -1) * m._stacks()["scale"]
+        g = torch.sub(drop(ones), 1, out=gs[i])
+        st = m._stacks()
+        u[i].add_(((x * g).view(B * T, d) @ st["A"][0].t()).view(B, T, -1), alpha=st["scale"])
     return gs
 
 
