@@ -14,9 +14,11 @@ collective).  Weights are random-init (no hub access), inputs synthetic.
 Beside the headline the line carries bounded extra legs under ``"extra"`` (``--extras none`` skips them):
   medium / large_v3   BASELINE configs[2] / [3] per-GPU shards (whisper-medium 4 x r32, whisper-large-v3 8 x r64, 64 clips
                       per GPU), a few steps each, with their own q|k|v+LoRA roofline;
-  train               BASELINE configs[4]: whisper-small LoRA r16 training step (fwd + LoRA-only bwd through K3, bf16 base,
-                      gradient checkpointing as in WhisperLoRA's default), 16 clips per GPU, NCCL all-reduce of the flat
-                      fp32 adapter-gradient bucket at N > 1 with its own time and bytes;
+  train               BASELINE configs[4]: whisper-small LoRA r16 training step (fused forward + backward layers, LoRA-only
+                      gradients through K3, bf16 base, gradient checkpointing as in WhisperLoRA's default, clip + AdamW),
+                      16 clips per GPU; `value` = the step replayed as one CUDA graph (GraphedTrainStep), `eager_value` =
+                      the reference trainer's loop as written; NCCL all-reduce of the flat fp32 adapter-gradient bucket
+                      at N > 1 with its own time and bytes;
   gpu_eager_baseline  (N = 1) the reference's per-utterance loop — HF Whisper + eager PEFT-formula LoRA — in bf16 on the
                       SAME B200 (oracle port moved to the GPU), on a bounded sample: what the kernels buy over torch eager.
 
